@@ -1,0 +1,203 @@
+/* loco_b200.h -- C ABI of the B200-native LOCO interpolation hot path.
+ *
+ * The reference (mit-gfx/LOCOInterpolate) has no FFI of its own: its boundary is the C++ class surface
+ * of LCSampledFunction / PrecomputedParametricShapeConverter, linked statically.  Each entry point below
+ * names the reference interface it stands in for (paths relative to the reference root); INTEGRATION.md
+ * shows the few lines a maintainer adds on the reference side to route a batch of queries through it.
+ *
+ * Conventions (mirroring LCError, LCUtils/LCError.h:7-20): every call returns 0 on success and a
+ * non-zero code otherwise; loco_last_error() then gives the description, using the reference's own
+ * message texts where the reference has one.  The caller owns every buffer it passes in.  A model handle
+ * is bound to ONE GPU and is not re-entrant (one call at a time per handle).  There is no CPU fallback:
+ * without a CUDA device every constructor fails with LOCO_ERR_CUDA.
+ *
+ * Numbering is canonical: leaf index = rank in LCAdaptiveGridCell::getAllLeafCells order
+ * (LCAdaptiveGridCell.cpp:247-258), sample index = position in LCSampledFunction::samples_ (= proto id,
+ * LCProtoConverter.cpp:147-152), tree cells in pre-order with child1 first (:131-133).
+ */
+#ifndef LOCO_B200_H
+#define LOCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct loco_model loco_model_t;
+
+enum {
+	LOCO_OK = 0,
+	LOCO_ERR_INVALID = 1,  /* bad argument / inconsistent graph (message has the detail) */
+	LOCO_ERR_IO = 2,       /* "could not open file ..." / "could not parse the file" */
+	LOCO_ERR_CUDA = 3,     /* no device, allocation or launch failure */
+	LOCO_ERR_RANGE = 4     /* index out of range / buffer too small */
+};
+
+/* `device` value that builds the host side of a model only (graph, flattening, support sets, proto I/O) for
+ * inspection on machines without a GPU.  Every evaluation call on such a handle fails with LOCO_ERR_CUDA. */
+#define LOCO_HOST_ONLY (-1)
+
+/* LCBasisFunction::LCBasisFunctionType (LCAdaptiveSampling/LCBasisFunction.h:19) */
+enum { LOCO_LINEAR_BSPLINE = 0, LOCO_CUBIC_BSPLINE = 1 };
+
+/* per-query status byte; the texts are the reference's LCError descriptions */
+enum {
+	LOCO_ST_OK = 0,
+	LOCO_ST_OUTSIDE_CELL = 1,     /* "parameter ouside cell"            LCAdaptiveGridCell.cpp:438-454 */
+	LOCO_ST_BAD_ARITY = 2,        /* "invalid number of parameters"     (raised by the C++ facade only) */
+	LOCO_ST_NO_COMMON_SAMPLE = 3, /* "could not find closest sample"    LCAdaptiveGridCell.cpp:533-538 */
+	LOCO_ST_EMPTY_SUPPORT = 4     /* "cannot create new from empty list of weighted samples" LCFunctionValue.cpp:14-17 */
+};
+
+/* Plain-array image of an LCSampledFunction object graph: what a reference-side binding fills from
+ * LCSampledFunction::{getRoot,getSamples,getBorderCells,getRanges} (LCSampledFunction.h:11-36).
+ * Cells: tree cells in pre-order (child1 = index+1), each with ranges_[2N]; a leaf has split_dir = -1. */
+typedef struct loco_graph {
+	int32_t n_params;            /* N */
+	int32_t value_dim;           /* D: 1 for LCRealFunctionValue, 3V for a V-vertex mesh value */
+	int32_t basis_type;          /* LOCO_LINEAR_BSPLINE / LOCO_CUBIC_BSPLINE (basisType_, LCSampledFunction.cpp:15) */
+	const double *domain;        /* [2N] ranges_ (min,max per parameter) */
+
+	int64_t n_samples;           /* S */
+	const double *sample_center; /* [S*N]  LCSample::center_ (cube coordinates) */
+	const double *sample_value;  /* [S*D]  LCSample::shapeInfo_ */
+	const int32_t *sample_value_group; /* [S] or NULL: samples sharing one LCFunctionValue object carry the same id */
+	const int64_t *bf_offset;    /* [S+1]  CSR: basisFunctions_ of each sample */
+	const double *bf_center;     /* [B*N]  LCBasisFunction::center_ */
+	const double *bf_support;    /* [B*N]  LCBasisFunction::support_ */
+	const double *bf_weight;     /* [B]    LCBasisFunction::weight_ */
+
+	int64_t n_cells;             /* C tree cells */
+	const double *cell_ranges;   /* [C*2N] */
+	const int32_t *cell_split_dir;   /* [C] splitDirection_, -1 for a leaf */
+	const double *cell_split_val;    /* [C] splitVal_ */
+	const int32_t *cell_child2;      /* [C] pre-order index of child2_, -1 for a leaf */
+	const double *cell_center_value; /* [C*D] or NULL: centerShapeInfo_ of leaves (true f at the cell centre) */
+	const int64_t *cell_sample_offset; /* [C+1] CSR: samples_ map of each leaf */
+	const int32_t *cell_sample;        /* sample index */
+	const double *cell_sample_value;   /* [E*D] or NULL: per-cell value copies (NULL = the sample's own value) */
+
+	int64_t n_border_cells;      /* border cells (cubic only; level -1, all leaves) */
+	const double *border_ranges; /* [Bc*2N] */
+	const double *border_center_value;   /* [Bc*D] or NULL */
+	const int64_t *border_sample_offset; /* [Bc+1] */
+	const int32_t *border_sample;
+	const double *border_sample_value;   /* or NULL */
+} loco_graph_t;
+
+typedef struct loco_info {
+	int32_t n_params, value_dim, basis_type, exact_rcp;
+	int32_t depth, max_support, max_terms, device;
+	int64_t n_samples, n_value_rows, n_leaves, n_cells, n_border_cells, n_basis_functions;
+	int64_t n_support_entries, n_terms, device_bytes;
+} loco_info_t;
+
+/* f : original parameter space [N] -> value [D]   (LCFunction::evalShapeInfo, LCFunction/LCFunction.h:32) */
+typedef void (*loco_value_fn)(const double *params, double *out, void *user);
+
+/* ---- construction ------------------------------------------------------------------------------ */
+
+/* PrecomputedParametricShapeConverter::loadFromProto(filename, useAscii, &shape)
+ * (LCAdaptiveSampling/LCProtoConverter.h:14, .cpp:26-33 -> convertToCplusplus :356-403 ->
+ * addAllNeighboursTopDown + LCSampledFunction::addBorderCells), then flatten + upload to `device`. */
+int loco_model_from_proto(const char *path, int ascii, int device, loco_model_t **out);
+
+/* new LCSampledFunction(root, ranges, samples, borderCells) + addBorderCells()
+ * (LCAdaptiveSampling/LCSampledFunction.cpp:9-47), from a plain-array graph. */
+int loco_model_from_graph(const loco_graph_t *graph, int device, loco_model_t **out);
+
+/* LCAdaptiveGrid(f, basis, LCAdaptiveSamplingParams(maxDepth <= N*level, ., level, .), evalCorners)
+ * restricted to its bootstrap phase (LCAdaptiveGrid.cpp:16-39 -> bootstrapSample :256-456), wrapped in an
+ * LCSampledFunction.  fn == NULL leaves the value table unset (use loco_model_fill_values_synthetic or
+ * loco_model_set_values); the true centre values needed by loco_center_error are then unavailable. */
+int loco_model_bootstrap(int32_t n_params, int32_t basis_type, int32_t level, int32_t value_dim, int32_t eval_corners,
+                         const double *domain, loco_value_fn fn, void *user, int device, loco_model_t **out);
+
+/* PrecomputedParametricShapeConverter::outputToProto(filename, useAscii, shape) (LCProtoConverter.cpp:14-24) */
+int loco_model_save_proto(const loco_model_t *m, const char *path, int ascii);
+
+void loco_free(loco_model_t *m);
+
+/* ---- introspection ------------------------------------------------------------------------------- */
+int loco_model_info(const loco_model_t *m, loco_info_t *info);
+
+/* Sorted sample indices of LCAdaptiveGridCell::getAllInfluencingSamples for a leaf
+ * (LCAdaptiveGridCell.cpp:558-607).  *k receives the count; LOCO_ERR_RANGE if cap is too small. */
+int loco_support_set(const loco_model_t *m, int32_t leaf, int32_t *ids, int32_t cap, int32_t *k);
+
+/* number of leaf / border-cell neighbours of a leaf (LCAdaptiveGridCell::getNeighbors, :93-96) */
+int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, int32_t *n_border);
+
+/* description of the last failure on this handle (or, with m == NULL, of the last failed constructor
+ * on this thread) -- LCError::internalDescription (LCUtils/LCError.cpp:13-16) */
+const char *loco_last_error(const loco_model_t *m);
+const char *loco_status_string(int status);
+
+/* ---- value table ----------------------------------------------------------------------------------- */
+/* replace the value table: rows [n_value_rows * value_dim], host memory */
+int loco_model_set_values(loco_model_t *m, const double *values);
+/* fill the table on the device with v[row][j] = sin(0.37*j + 0.61*row + seed) + 0.001*(j % 97)
+ * (synthetic mesh tables for benchmarks; never materialised on the host) */
+int loco_model_fill_values_synthetic(loco_model_t *m, double seed);
+/* copy rows [row0, row0+n) to host */
+int loco_model_get_values(const loco_model_t *m, int64_t row0, int64_t n, double *out);
+
+/* ---- the hot path ------------------------------------------------------------------------------------
+ * LCSampledFunction::evalShapeInfo(params, &result) (LCSampledFunction.cpp:69-78) for a batch:
+ *   mapToStandardHypercube (LCFunction.cpp:59-73) -> getCointainingLeaf (LCAdaptiveGridCell.cpp:260-272)
+ *   -> evalPametersAreInCell (:438-454) -> LCAdaptiveGridCell::evalShapeInfo (:611-676):
+ *   getInterpolationWeight (LCSample.cpp:76-89) over LCLinearBSpline/LCCubicBSpline::eval
+ *   (LCBasisFunction.cpp:273-293, 380-419) -> LCFunctionValue::newFromWeightedSum (LCFunctionValue.cpp:11-32).
+ * q: [Q*N] row-major in ORIGINAL parameter space.  out: [Q*D] (NaN where status != 0).
+ * leaf: [Q] containing leaf (or NULL).  status: [Q] LOCO_ST_* (or NULL). */
+
+/* host buffers; host<->device copies are pipelined with the kernels inside the call */
+int loco_eval_batch(loco_model_t *m, const double *q, int64_t n_queries, double *out, int32_t *leaf, uint8_t *status);
+
+/* device buffers on the model's GPU; asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
+int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t n_queries, double *out, int32_t *leaf,
+                           uint8_t *status, void *cuda_stream);
+
+/* mesh-valued batches too large to keep: evaluate but store only a per-query checksum
+ * sum_j out[q][j] * (1 + (j % 7))   -> checksum [Q]; `ring` is a device scratch of ring_queries*D doubles
+ * that the results are streamed through (every output element is written to HBM exactly once). */
+int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t n_queries, double *ring, int64_t ring_queries,
+                                double *checksum, int32_t *leaf, uint8_t *status, void *cuda_stream);
+
+/* ---- refinement-loop error check ---------------------------------------------------------------------
+ * The data-parallel part of LCAdaptiveGrid::decideSplit (LCAdaptiveGrid.cpp:578-626) with
+ * LCRealFunctionValue::computeErrorVector (LCRealFunctionValue.cpp:37-47): evaluate the interpolant at P
+ * points, err = |approx - truth| component-wise, per containing leaf keep the max error and
+ * split = !(max(err - threshold) <= 0) OR-reduced (NaN => split).
+ * q [P*N] original space, truth [P*D]; err_max [L] and split [L] are OVERWRITTEN (leaves without points:
+ * 0 / 0).  Points whose status != 0 are skipped and counted in *n_bad (may be NULL). */
+int loco_error_check(loco_model_t *m, const double *q, const double *truth, int64_t n_points, double threshold,
+                     double *err_max, uint8_t *split, int64_t *n_bad);
+int loco_error_check_device(loco_model_t *m, const double *q, const double *truth, int64_t n_points, double threshold,
+                            double *err_max, uint8_t *split, int64_t *n_bad_dev, void *cuda_stream);
+
+/* CENTER_BASED metric (LCAdaptiveGrid.cpp:594-602, LCAdaptiveGridCell::getApproximationError :1088-1100):
+ * interpolant at every leaf centre against the stored centerShapeInfo_.  err_max/split: [L] host. */
+int loco_center_error(loco_model_t *m, double threshold, double *err_max, uint8_t *split);
+
+/* RANDOM_SAMPLES metric at scale (LCAdaptiveGrid.cpp:603-619 with getJitterPoint :564-575): points_per_leaf
+ * jitter points per leaf are generated ON THE DEVICE from a counter-based generator (leaf, i, seed), the
+ * truth is the reference's test function family f(x) = 1 + sum_i sum_j a[i][j] * sin(3*j*x_i + p[i][j])
+ * (LCRealFunction.cpp:50-63) with coefficients amp/phase [N*n_terms] supplied by the caller.
+ * err_max/split: [L] device. */
+int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, uint64_t seed, const double *amp,
+                                      const double *phase, int32_t n_terms, double threshold, double *err_max,
+                                      uint8_t *split, void *cuda_stream);
+
+/* ---- tuning / accounting -------------------------------------------------------------------------------- */
+/* options: "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted tiles;  "fp32" 0|1 (scalar weights in fp32) */
+int loco_set_option(loco_model_t *m, const char *name, int64_t value);
+/* kernels launched by this handle since creation (for bench accounting) */
+int64_t loco_kernel_launches(const loco_model_t *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCO_B200_H */

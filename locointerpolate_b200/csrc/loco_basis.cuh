@@ -1,0 +1,115 @@
+// loco_basis.cuh -- device building blocks shared by all evaluation kernels.
+#pragma once
+#include "loco_device.h"
+
+namespace loco {
+
+// Query coordinates in registers.  NT > 0: fully unrolled, dynamic reads (the split dimension during
+// descent) become a select chain.  NT == 0: runtime N <= kMaxN, coordinates live in local memory.
+template <int NT>
+struct Coord {
+	double v[NT > 0 ? NT : kMaxN];
+	__device__ __forceinline__ void set(int d, double val)
+	{
+		if (NT > 0) {
+#pragma unroll
+			for (int i = 0; i < (NT > 0 ? NT : 1); i++) if (i == d) v[i] = val;
+		} else v[d] = val;
+	}
+	__device__ __forceinline__ double get(int d) const
+	{
+		if (NT > 0) {
+			double r = v[0];
+#pragma unroll
+			for (int i = 1; i < (NT > 0 ? NT : 1); i++) r = (i == d) ? v[i] : r;
+			return r;
+		}
+		return v[d];
+	}
+};
+
+// LCFunction::mapToStandardHypercube (LCFunction.cpp:59-73): alpha = (p-min)/(max-min); x = alpha*2 - 1.
+// Explicit _rn intrinsics: no contraction, IEEE division -- the leaf index depends on every bit of x.
+template <int NT>
+__device__ __forceinline__ void map_to_cube(const DeviceModel &m, const double *__restrict__ p, Coord<NT> &x)
+{
+	const int N = NT > 0 ? NT : m.N;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double mn = m.dom_min[d], mx = m.dom_max[d];
+		const double alpha = __ddiv_rn(__dsub_rn(p[d], mn), __dsub_rn(mx, mn));
+		x.set(d, __dsub_rn(__dmul_rn(alpha, 2.0), 1.0));
+	}
+}
+
+// LCAdaptiveGridCell::getCointainingLeaf (LCAdaptiveGridCell.cpp:260-272): strict '<' sends ties to child2.
+// One 16-byte read-only load per level; child1 is the next cell in pre-order.
+template <int NT>
+__device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT> &x)
+{
+	int32_t c = 0;
+	for (;;) {
+		const int4 raw = __ldg(reinterpret_cast<const int4 *>(m.cells + c));
+		if (raw.z < 0) return raw.w;
+		const double split = __hiloint2double(raw.y, raw.x);
+		c = (x.get(raw.z) < split) ? c + 1 : raw.w;
+	}
+}
+
+// LCAdaptiveGridCell::evalPametersAreInCell (:438-454) against lo-EPSILON / hi+EPSILON precomputed on the
+// host with the reference's own double operations.
+template <int NT>
+__device__ __forceinline__ uint8_t containment_status(const DeviceModel &m, const Coord<NT> &x, int32_t leaf)
+{
+	const int N = NT > 0 ? NT : m.N;
+	bool outside = false;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double xv = x.get(d);
+		outside |= (xv < m.leaf_lo_eps[(int64_t)leaf * N + d]) || (xv > m.leaf_hi_eps[(int64_t)leaf * N + d]);
+	}
+	return outside ? (uint8_t)ST_OUTSIDE_CELL : (uint8_t)ST_OK;
+}
+
+// One dimension of LCLinearBSpline::eval (LCBasisFunction.cpp:283-288): d = |x-c|/s; d <= 1 ? 1-d : 0.
+// u = (x-c)/s is passed in.
+__device__ __forceinline__ double linear_1d(double u)
+{
+	const double d = fabs(u);
+	return d <= 1.0 ? 1.0 - d : 0.0;
+}
+
+// One dimension of LCCubicBSpline::eval (LCBasisFunction.cpp:390-414).  The reference selects one of four
+// pieces with k = floor(2(u+1)), t = 1-(2(u+1)-k); the uniform cubic B-spline is even in u, so with
+// v = 2|u| the pieces k=1,2 are (3v^3 - 6v^2 + 4)/6 and the pieces k=0,3 are (2-v)^3/6 -- the same
+// polynomials evaluated without the floor and with two branches instead of four.  Differs from the
+// reference's expression by rounding only (a few ulp of a value <= 2/3); |u| > 1 and NaN give 0.
+__device__ __forceinline__ double cubic_1d(double u)
+{
+	const double v = 2.0 * fabs(u);
+	const double inner = fma(v * v, fma(3.0, v, -6.0), 4.0);
+	const double w = 2.0 - v;
+	const double outer = w * w * w;
+	const double r = v < 1.0 ? inner : (v <= 2.0 ? outer : 0.0);
+	return r * (1.0 / 6.0);
+}
+
+// LC{Linear,Cubic}BSpline::eval: value = prod_i dimVal_i, result = value * weight_.
+// cs = (c_0, s_0, c_1, s_1, ...) with s_i replaced by 1/s_i when EXACT (every support a power of two,
+// so the product is bit-identical to the division).
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double term_value(const double *__restrict__ cs, double weight, const Coord<NT> &x, int Nrt)
+{
+	const int N = NT > 0 ? NT : Nrt;
+	double value = 1.0;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double2 c = __ldg(reinterpret_cast<const double2 *>(cs) + d);
+		const double diff = x.get(d) - c.x;
+		const double u = EXACT ? diff * c.y : diff / c.y;
+		value *= CUBIC ? cubic_1d(u) : linear_1d(u);
+	}
+	return value * weight;
+}
+
+} // namespace loco

@@ -1,0 +1,588 @@
+// loco_capi.cu -- implementation of the C ABI declared in include/loco_b200.h.
+//
+// Host orchestration only: builds the Graph (from a proto file, a plain-array graph or the bootstrap
+// generator), flattens it, uploads the flat model once, and drives the kernels.  There is no CPU
+// evaluation path in this library: if no CUDA device is usable every constructor fails.
+#include "../../include/loco_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "loco_bootstrap.h"
+#include "loco_device.h"
+#include "loco_flat.h"
+#include "loco_proto.h"
+
+using namespace loco;
+
+namespace {
+
+thread_local std::string g_ctor_error = "no error";
+
+const int kSlots = 3;  // pipeline depth of the host-buffer path
+
+struct Workspace {
+	cudaStream_t stream = nullptr;
+	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr;
+	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0;
+};
+
+} // namespace
+
+struct loco_model {
+	int device = 0;
+	bool host_only = false;  // device == LOCO_HOST_ONLY: introspection only, every evaluation call fails
+	Graph graph;
+	Flat flat;
+	DeviceModel dm{};
+	std::vector<void *> allocs;
+	double *d_values = nullptr;
+	int64_t device_bytes = 0;
+	mutable std::string err = "no error";
+	int64_t launches = 0;
+	int64_t opt_path = 0, opt_fp32 = 0;
+	Workspace ws[kSlots];
+};
+
+namespace {
+
+int fail(const loco_model *m, int code, const std::string &msg)
+{
+	if (m) m->err = msg;
+	else g_ctor_error = msg;
+	return code;
+}
+
+#define NEED_DEVICE(m) do { if ((m)->host_only) return fail(m, LOCO_ERR_CUDA, "model is host-only (LOCO_HOST_ONLY): evaluation needs a CUDA device, there is no CPU path"); } while (0)
+
+#define CUDA_OK(m, expr)                                                                                   \
+	do {                                                                                                   \
+		cudaError_t _e = (expr);                                                                           \
+		if (_e != cudaSuccess) return fail(m, LOCO_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(_e)); \
+	} while (0)
+
+template <typename T>
+int upload(loco_model *m, const std::vector<T> &h, const T **dptr, size_t min_elems = 1)
+{
+	size_t n = std::max(h.size(), min_elems);
+	void *d = nullptr;
+	CUDA_OK(m, cudaMalloc(&d, n * sizeof(T)));
+	m->allocs.push_back(d);
+	m->device_bytes += (int64_t)(n * sizeof(T));
+	if (!h.empty()) CUDA_OK(m, cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+	*dptr = static_cast<const T *>(d);
+	return LOCO_OK;
+}
+
+int grow(loco_model *m, void **p, size_t *have, size_t need)
+{
+	if (need <= *have) return LOCO_OK;
+	if (*p) { CUDA_OK(m, cudaFree(*p)); *p = nullptr; *have = 0; }
+	need = need + need / 4 + 256;
+	CUDA_OK(m, cudaMalloc(p, need));
+	*have = need;
+	return LOCO_OK;
+}
+
+template <typename T>
+std::vector<int32_t> narrow(loco_model *m, const std::vector<T> &v, bool *ok)
+{
+	std::vector<int32_t> r(v.size());
+	for (size_t i = 0; i < v.size(); i++) {
+		if (v[i] > (T)0x7fffffff) *ok = false;
+		r[i] = (int32_t)v[i];
+	}
+	(void)m;
+	return r;
+}
+
+int build_device_model(loco_model *m)
+{
+	if (m->device == LOCO_HOST_ONLY) {
+		m->host_only = true;
+		m->dm.N = m->flat.N; m->dm.D = m->flat.D; m->dm.L = (int32_t)m->flat.L; m->dm.R = m->flat.R;
+		return LOCO_OK;
+	}
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(m, LOCO_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
+	if (m->device < 0 || m->device >= ndev) return fail(m, LOCO_ERR_CUDA, "device index out of range");
+	CUDA_OK(m, cudaSetDevice(m->device));
+	Flat &f = m->flat;
+	if (f.N > kMaxN) return fail(m, LOCO_ERR_INVALID, "more than 16 parameters are not supported");
+	if (f.L > 0x7fffffff || f.C > 0x7fffffff) return fail(m, LOCO_ERR_INVALID, "tree too large");
+	DeviceModel &dm = m->dm;
+	dm.N = f.N; dm.D = f.D; dm.basis = f.basis; dm.exact_rcp = f.exact_rcp ? 1 : 0;
+	dm.L = (int32_t)f.L; dm.C = (int32_t)f.C; dm.max_support = std::max(f.max_support, 1); dm.max_terms = f.max_terms;
+	dm.R = f.R;
+	dm.value_stride = f.D == 1 ? 1 : ((f.D + 1) / 2) * 2;  // rows 16-byte aligned for 128-bit loads
+	bool ok = true;
+	std::vector<int32_t> sup_off = narrow(m, f.sup_off, &ok), term_off = narrow(m, f.term_off, &ok);
+	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
+	int rc;
+	if ((rc = upload(m, f.dom_min, &dm.dom_min))) return rc;
+	if ((rc = upload(m, f.dom_max, &dm.dom_max))) return rc;
+	if ((rc = upload(m, f.cells, &dm.cells))) return rc;
+	if ((rc = upload(m, f.leaf_lo_eps, &dm.leaf_lo_eps))) return rc;
+	if ((rc = upload(m, f.leaf_hi_eps, &dm.leaf_hi_eps))) return rc;
+	if ((rc = upload(m, f.leaf_lo, &dm.leaf_lo))) return rc;
+	if ((rc = upload(m, f.leaf_hi, &dm.leaf_hi))) return rc;
+	if ((rc = upload(m, f.leaf_status, &dm.leaf_status))) return rc;
+	if ((rc = upload(m, f.leaf_center_row, &dm.leaf_center_row))) return rc;
+	if ((rc = upload(m, sup_off, &dm.sup_off))) return rc;
+	if ((rc = upload(m, f.sup_row, &dm.sup_row))) return rc;
+	if ((rc = upload(m, term_off, &dm.term_off))) return rc;
+	if ((rc = upload(m, f.term_cs, &dm.term_cs, 2))) return rc;
+	if ((rc = upload(m, f.term_w, &dm.term_w))) return rc;
+	if ((rc = upload(m, f.term_slot, &dm.term_slot))) return rc;
+	if ((rc = upload(m, f.term_row, &dm.term_row))) return rc;
+	// value table
+	size_t vbytes = (size_t)std::max<int64_t>(f.R, 1) * dm.value_stride * sizeof(double);
+	CUDA_OK(m, cudaMalloc((void **)&m->d_values, vbytes));
+	m->allocs.push_back(m->d_values);
+	m->device_bytes += (int64_t)vbytes;
+	CUDA_OK(m, cudaMemset(m->d_values, 0, vbytes));
+	dm.values = m->d_values;
+	if (!f.values.empty()) {
+		if ((rc = loco_model_set_values(m, f.values.data()))) return rc;
+	}
+	// the big term arrays are only needed on the device
+	std::vector<double>().swap(f.term_cs);
+	std::vector<double>().swap(f.term_w);
+	std::vector<int32_t>().swap(f.term_slot);
+	std::vector<int32_t>().swap(f.term_row);
+	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamCreateWithFlags(&m->ws[s].stream, cudaStreamNonBlocking));
+	return LOCO_OK;
+}
+
+int finish_model(loco_model *m, int device, loco_model_t **out)
+{
+	m->device = device;
+	Status s = flatten(m->graph, &m->flat);
+	if (!s.ok) { int rc = fail(nullptr, LOCO_ERR_INVALID, s.msg); loco_free(m); return rc; }
+	int rc = build_device_model(m);
+	if (rc) { g_ctor_error = m->err; loco_free(m); return rc; }
+	*out = m;
+	return LOCO_OK;
+}
+
+// scalar or mesh evaluation of Q queries resident on the device, using workspace slot `w`
+int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, const double *q, int64_t Q, double *out, int64_t out_stride,
+                int32_t *leaf, uint8_t *status)
+{
+	const DeviceModel &dm = m->dm;
+	if (Q <= 0) return LOCO_OK;
+	if (dm.D == 1) {
+		m->launches += in_cube ? launch_eval_scalar_in_cube(dm, q, Q, out, leaf, status, st) : launch_eval_scalar_direct(dm, q, Q, out, leaf, status, st);
+		CUDA_OK(m, cudaGetLastError());
+		return LOCO_OK;
+	}
+	// mesh-valued: weights, then the weighted gather-sum, in chunks that bound the weight scratch
+	const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(Q, ((int64_t)256 << 20) / ((int64_t)dm.max_support * 8)));
+	int rc;
+	if ((rc = grow(m, &w.W, &w.W_b, (size_t)chunk * dm.max_support * sizeof(double)))) return rc;
+	if (!leaf && !in_cube) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+	if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+	for (int64_t o = 0; o < Q; o += chunk) {
+		const int64_t n = std::min(chunk, Q - o);
+		m->launches += in_cube ? launch_weights_in_cube(dm, q + o * dm.N, n, (double *)w.W, leaf + o, status + o, st)
+		                       : launch_weights(dm, q + o * dm.N, n, (double *)w.W, leaf + o, status + o, st);
+		m->launches += launch_mesh_gather(dm, (const double *)w.W, leaf + o, status + o, n, out + o * out_stride, out_stride, st);
+	}
+	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+int loco_model_from_proto(const char *path, int ascii, int device, loco_model_t **out)
+{
+	if (!path || !out) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	*out = nullptr;
+	loco_model *m = new loco_model();
+	Status s = read_proto_file(path, ascii != 0, &m->graph);
+	if (!s.ok) {
+		delete m;
+		bool io = s.msg.rfind("could not open", 0) == 0 || s.msg == "could not parse the file";
+		return fail(nullptr, io ? LOCO_ERR_IO : LOCO_ERR_INVALID, s.msg);
+	}
+	return finish_model(m, device, out);
+}
+
+int loco_model_from_graph(const loco_graph_t *gd, int device, loco_model_t **out)
+{
+	if (!gd || !out) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	*out = nullptr;
+	const int N = gd->n_params, D = gd->value_dim;
+	if (N < 1 || D < 1) return fail(nullptr, LOCO_ERR_INVALID, "invalid number of parameters");
+	if (!gd->domain || !gd->sample_center || !gd->sample_value || !gd->bf_offset || !gd->cell_ranges || !gd->cell_split_dir ||
+	    !gd->cell_split_val || !gd->cell_child2 || !gd->cell_sample_offset)
+		return fail(nullptr, LOCO_ERR_INVALID, "null array in graph description");
+	loco_model *m = new loco_model();
+	Graph &g = m->graph;
+	g.N = N; g.D = D; g.basis = gd->basis_type;
+	g.domain.assign(gd->domain, gd->domain + 2 * N);
+	const int64_t S = gd->n_samples;
+	g.sample_center.assign(gd->sample_center, gd->sample_center + S * N);
+	// value rows: one per value object (samples of one group share a row)
+	std::unordered_map<int32_t, int32_t> group_row;
+	g.sample_row.resize((size_t)S);
+	for (int64_t s = 0; s < S; s++) {
+		if (gd->sample_value_group) {
+			auto it = group_row.find(gd->sample_value_group[s]);
+			if (it != group_row.end()) { g.sample_row[(size_t)s] = it->second; continue; }
+			group_row[gd->sample_value_group[s]] = (int32_t)g.n_rows();
+		}
+		g.sample_row[(size_t)s] = (int32_t)g.n_rows();
+		g.values.insert(g.values.end(), gd->sample_value + s * D, gd->sample_value + (s + 1) * D);
+	}
+	g.bf_off.assign(gd->bf_offset, gd->bf_offset + S + 1);
+	const int64_t B = S > 0 ? gd->bf_offset[S] : 0;
+	if (B > 0 && (!gd->bf_center || !gd->bf_support || !gd->bf_weight)) { delete m; return fail(nullptr, LOCO_ERR_INVALID, "null basis function arrays"); }
+	g.bf_center.assign(gd->bf_center, gd->bf_center + B * N);
+	g.bf_support.assign(gd->bf_support, gd->bf_support + B * N);
+	g.bf_weight.assign(gd->bf_weight, gd->bf_weight + B);
+	auto fill_cells = [&](Graph::CellSet &cs, int64_t C, const double *ranges, const int32_t *split_dir, const double *split_val,
+	                      const int32_t *child2, const double *center_value, const int64_t *off, const int32_t *sample, const double *copy) -> bool {
+		cs.ranges.assign(ranges, ranges + C * 2 * N);
+		cs.split_dir.resize((size_t)C); cs.split_val.resize((size_t)C); cs.child2.resize((size_t)C); cs.center_row.assign((size_t)C, -1);
+		for (int64_t c = 0; c < C; c++) {
+			cs.split_dir[(size_t)c] = split_dir ? split_dir[c] : -1;
+			cs.split_val[(size_t)c] = split_val ? split_val[c] : 0.0;
+			cs.child2[(size_t)c] = child2 ? child2[c] : -1;
+			if (center_value && cs.split_dir[(size_t)c] < 0) {
+				cs.center_row[(size_t)c] = (int32_t)g.n_rows();
+				g.values.insert(g.values.end(), center_value + c * D, center_value + (c + 1) * D);
+			}
+		}
+		cs.ls_off.assign(off, off + C + 1);
+		const int64_t E = off[C];
+		cs.ls_sample.assign(sample, sample + E);
+		cs.ls_row.resize((size_t)E);
+		for (int64_t e = 0; e < E; e++) {
+			int32_t s = sample[e];
+			if (s < 0 || s >= S) return false;
+			int32_t sr = g.sample_row[(size_t)s];
+			if (!copy || memcmp(copy + e * D, &g.values[(size_t)sr * D], sizeof(double) * D) == 0) cs.ls_row[(size_t)e] = sr;
+			else {
+				cs.ls_row[(size_t)e] = (int32_t)g.n_rows();
+				g.values.insert(g.values.end(), copy + e * D, copy + (e + 1) * D);
+			}
+		}
+		return true;
+	};
+	bool ok = fill_cells(g.tree, gd->n_cells, gd->cell_ranges, gd->cell_split_dir, gd->cell_split_val, gd->cell_child2, gd->cell_center_value,
+	                     gd->cell_sample_offset, gd->cell_sample, gd->cell_sample_value);
+	if (ok && gd->n_border_cells > 0) {
+		if (!gd->border_ranges || !gd->border_sample_offset) ok = false;
+		else ok = fill_cells(g.border, gd->n_border_cells, gd->border_ranges, nullptr, nullptr, nullptr, gd->border_center_value,
+		                     gd->border_sample_offset, gd->border_sample, gd->border_sample_value);
+	} else if (ok) g.border.ls_off.assign(1, 0);
+	if (!ok) { delete m; return fail(nullptr, LOCO_ERR_INVALID, "could not map the sample from id"); }
+	return finish_model(m, device, out);
+}
+
+int loco_model_bootstrap(int32_t n_params, int32_t basis_type, int32_t level, int32_t value_dim, int32_t eval_corners, const double *domain,
+                         loco_value_fn fn, void *user, int device, loco_model_t **out)
+{
+	if (!domain || !out) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	*out = nullptr;
+	loco_model *m = new loco_model();
+	Status s = bootstrap_graph(n_params, basis_type, level, value_dim, eval_corners != 0, domain, fn, user, &m->graph);
+	if (!s.ok) { delete m; return fail(nullptr, LOCO_ERR_INVALID, s.msg); }
+	return finish_model(m, device, out);
+}
+
+int loco_model_save_proto(const loco_model_t *m, const char *path, int ascii)
+{
+	if (!m || !path) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (m->graph.values.empty()) return fail(m, LOCO_ERR_INVALID, "undefined type of shape info");  // value table lives only on the device
+	Status s = write_proto_file(m->graph, path, ascii != 0);
+	if (!s.ok) return fail(m, s.msg.rfind("could not write", 0) == 0 ? LOCO_ERR_IO : LOCO_ERR_INVALID, s.msg);
+	return LOCO_OK;
+}
+
+void loco_free(loco_model_t *m)
+{
+	if (!m) return;
+	if (!m->host_only && (!m->allocs.empty() || m->ws[0].stream)) cudaSetDevice(m->device);
+	for (void *p : m->allocs) cudaFree(p);
+	for (int s = 0; s < kSlots; s++) {
+		Workspace &w = m->ws[s];
+		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc}) if (p) cudaFree(p);
+		if (w.stream) cudaStreamDestroy(w.stream);
+	}
+	delete m;
+}
+
+int loco_model_info(const loco_model_t *m, loco_info_t *info)
+{
+	if (!m || !info) return fail(m, LOCO_ERR_INVALID, "null argument");
+	const Flat &f = m->flat;
+	memset(info, 0, sizeof(*info));
+	info->n_params = f.N; info->value_dim = f.D; info->basis_type = f.basis; info->exact_rcp = f.exact_rcp;
+	info->depth = f.depth; info->max_support = f.max_support; info->max_terms = f.max_terms; info->device = m->device;
+	info->n_samples = f.S; info->n_value_rows = f.R; info->n_leaves = f.L; info->n_cells = f.C;
+	info->n_border_cells = m->graph.border.size();
+	info->n_basis_functions = m->graph.bf_off.empty() ? 0 : m->graph.bf_off.back();
+	info->n_support_entries = f.sup_off.back();
+	info->n_terms = f.term_off.back();
+	info->device_bytes = m->device_bytes;
+	return LOCO_OK;
+}
+
+int loco_support_set(const loco_model_t *m, int32_t leaf, int32_t *ids, int32_t cap, int32_t *k)
+{
+	if (!m || !k) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (leaf < 0 || leaf >= m->flat.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	const int64_t a = m->flat.sup_off[(size_t)leaf], b = m->flat.sup_off[(size_t)leaf + 1];
+	*k = (int32_t)(b - a);
+	if (!ids) return LOCO_OK;
+	if (cap < b - a) return fail(m, LOCO_ERR_RANGE, "support buffer too small");
+	std::copy(m->flat.sup_sample.begin() + a, m->flat.sup_sample.begin() + b, ids);
+	return LOCO_OK;
+}
+
+int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, int32_t *n_border)
+{
+	if (!m) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (leaf < 0 || leaf >= m->flat.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	if (n_leaf) *n_leaf = m->flat.n_leaf_neighbors[(size_t)leaf];
+	if (n_border) *n_border = m->flat.n_border_neighbors[(size_t)leaf];
+	return LOCO_OK;
+}
+
+const char *loco_last_error(const loco_model_t *m) { return m ? m->err.c_str() : g_ctor_error.c_str(); }
+const char *loco_status_string(int status) { return status_string(status); }
+
+// ---- value table -------------------------------------------------------------------------------------
+int loco_model_set_values(loco_model_t *m, const double *values)
+{
+	if (!m || !values) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	CUDA_OK(m, cudaMemcpy2D(m->d_values, (size_t)dm.value_stride * sizeof(double), values, (size_t)dm.D * sizeof(double),
+	                        (size_t)dm.D * sizeof(double), (size_t)dm.R, cudaMemcpyHostToDevice));
+	return LOCO_OK;
+}
+
+int loco_model_fill_values_synthetic(loco_model_t *m, double seed)
+{
+	if (!m) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	m->launches += launch_fill_values(m->d_values, m->dm.R, m->dm.D, m->dm.value_stride, seed, nullptr);
+	CUDA_OK(m, cudaGetLastError());
+	CUDA_OK(m, cudaDeviceSynchronize());
+	return LOCO_OK;
+}
+
+int loco_model_get_values(const loco_model_t *m, int64_t row0, int64_t n, double *out)
+{
+	if (!m || !out) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (row0 < 0 || n < 0 || row0 + n > m->dm.R) return fail(m, LOCO_ERR_RANGE, "value row out of range");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	CUDA_OK(m, cudaMemcpy2D(out, (size_t)dm.D * sizeof(double), m->d_values + row0 * dm.value_stride, (size_t)dm.value_stride * sizeof(double),
+	                        (size_t)dm.D * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost));
+	return LOCO_OK;
+}
+
+// ---- hot path ---------------------------------------------------------------------------------------------
+int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, void *cuda_stream)
+{
+	if (!m || (Q > 0 && (!q || !out))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	return eval_device(m, m->ws[0], (cudaStream_t)cuda_stream, false, q, Q, out, m->dm.D, leaf, status);
+}
+
+int loco_eval_batch(loco_model_t *m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status)
+{
+	if (!m || (Q > 0 && (!q || !out))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	// chunk so that one slot's output stays <= 128 MB; three slots overlap H2D, kernels and D2H
+	int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)4 << 20, ((int64_t)128 << 20) / ((int64_t)dm.D * 8)));
+	chunk = std::min(chunk, std::max<int64_t>(Q, 1));
+	int rc;
+	int slot = 0;
+	for (int64_t o = 0; o < Q; o += chunk, slot = (slot + 1) % kSlots) {
+		const int64_t n = std::min(chunk, Q - o);
+		Workspace &w = m->ws[slot];
+		CUDA_OK(m, cudaStreamSynchronize(w.stream));  // the slot's previous chunk must have drained before its buffers are reused
+		if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
+		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * dm.D * 8))) return rc;
+		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
+		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
+		CUDA_OK(m, cudaMemcpyAsync(w.q, q + o * dm.N, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
+		if ((rc = eval_device(m, w, w.stream, false, (const double *)w.q, n, (double *)w.out, dm.D, (int32_t *)w.leaf, (uint8_t *)w.status))) return rc;
+		CUDA_OK(m, cudaMemcpyAsync(out + o * dm.D, w.out, (size_t)n * dm.D * 8, cudaMemcpyDeviceToHost, w.stream));
+		if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
+		if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+	}
+	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamSynchronize(m->ws[s].stream));
+	return LOCO_OK;
+}
+
+int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t Q, double *ring, int64_t ring_queries, double *checksum,
+                                int32_t *leaf, uint8_t *status, void *cuda_stream)
+{
+	if (!m || (Q > 0 && (!q || !ring || !checksum)) || ring_queries < 1) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	int rc;
+	for (int64_t o = 0; o < Q; o += ring_queries) {
+		const int64_t n = std::min(ring_queries, Q - o);
+		if ((rc = eval_device(m, m->ws[0], st, false, q + o * dm.N, n, ring, dm.value_stride, leaf ? leaf + o : nullptr, status ? status + o : nullptr))) return rc;
+		m->launches += launch_checksum(ring, dm.value_stride, dm.D, n, checksum + o, st);
+	}
+	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+// ---- error check ----------------------------------------------------------------------------------------------
+int loco_error_check_device(loco_model_t *m, const double *q, const double *truth, int64_t P, double threshold, double *err_max, uint8_t *split,
+                            int64_t *n_bad_dev, void *cuda_stream)
+{
+	if (!m || !err_max || !split || (P > 0 && (!q || !truth))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	Workspace &w = m->ws[0];
+	CUDA_OK(m, cudaMemsetAsync(err_max, 0, (size_t)dm.L * 8, st));
+	CUDA_OK(m, cudaMemsetAsync(split, 0, (size_t)dm.L, st));
+	if (n_bad_dev) CUDA_OK(m, cudaMemsetAsync(n_bad_dev, 0, 8, st));
+	const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)8 << 20, ((int64_t)256 << 20) / ((int64_t)dm.D * 8)));
+	int rc;
+	for (int64_t o = 0; o < P; o += chunk) {
+		const int64_t n = std::min(chunk, P - o);
+		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * dm.D * 8))) return rc;
+		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
+		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
+		if ((rc = eval_device(m, w, st, false, q + o * dm.N, n, (double *)w.out, dm.D, (int32_t *)w.leaf, (uint8_t *)w.status))) return rc;
+		m->launches += launch_error_reduce(dm, (const double *)w.out, truth + o * dm.D, (const int32_t *)w.leaf, (const uint8_t *)w.status, n, threshold,
+		                                   err_max, split, (unsigned long long *)n_bad_dev, st);
+	}
+	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+int loco_error_check(loco_model_t *m, const double *q, const double *truth, int64_t P, double threshold, double *err_max, uint8_t *split, int64_t *n_bad)
+{
+	if (!m || !err_max || !split || (P > 0 && (!q || !truth))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	void *dq = nullptr, *dt = nullptr, *de = nullptr, *ds = nullptr, *db = nullptr;
+	int rc = LOCO_OK;
+	cudaStream_t st = m->ws[1].stream;
+	do {
+		if (cudaMalloc(&dq, std::max<size_t>((size_t)P * dm.N * 8, 8)) || cudaMalloc(&dt, std::max<size_t>((size_t)P * dm.D * 8, 8)) ||
+		    cudaMalloc(&de, (size_t)dm.L * 8) || cudaMalloc(&ds, (size_t)dm.L) || cudaMalloc(&db, 8)) { rc = fail(m, LOCO_ERR_CUDA, "cudaMalloc failed in loco_error_check"); break; }
+		cudaMemcpyAsync(dq, q, (size_t)P * dm.N * 8, cudaMemcpyHostToDevice, st);
+		cudaMemcpyAsync(dt, truth, (size_t)P * dm.D * 8, cudaMemcpyHostToDevice, st);
+		if ((rc = loco_error_check_device(m, (const double *)dq, (const double *)dt, P, threshold, (double *)de, (uint8_t *)ds, (int64_t *)db, st))) break;
+		cudaMemcpyAsync(err_max, de, (size_t)dm.L * 8, cudaMemcpyDeviceToHost, st);
+		cudaMemcpyAsync(split, ds, (size_t)dm.L, cudaMemcpyDeviceToHost, st);
+		if (n_bad) cudaMemcpyAsync(n_bad, db, 8, cudaMemcpyDeviceToHost, st);
+		cudaError_t e = cudaStreamSynchronize(st);
+		if (e != cudaSuccess) rc = fail(m, LOCO_ERR_CUDA, cudaGetErrorString(e));
+	} while (0);
+	for (void *p : {dq, dt, de, ds, db}) if (p) cudaFree(p);
+	return rc;
+}
+
+int loco_center_error(loco_model_t *m, double threshold, double *err_max, uint8_t *split)
+{
+	if (!m || !err_max || !split) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	for (int64_t l = 0; l < m->flat.L; l++)
+		if (m->flat.leaf_center_row[(size_t)l] < 0) return fail(m, LOCO_ERR_INVALID, "model has no centre values (centerShapeInfo_)");
+	const int64_t L = dm.L;
+	Workspace &w = m->ws[1];
+	cudaStream_t st = w.stream;
+	int rc;
+	if ((rc = grow(m, &w.q, &w.q_b, (size_t)L * dm.N * 8))) return rc;
+	if ((rc = grow(m, &w.out, &w.out_b, (size_t)L * dm.D * 8))) return rc;
+	if ((rc = grow(m, &w.truth, &w.truth_b, (size_t)L * dm.D * 8))) return rc;
+	if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)L * 4))) return rc;
+	if ((rc = grow(m, &w.status, &w.status_b, (size_t)L))) return rc;
+	if ((rc = grow(m, &w.misc, &w.misc_b, (size_t)L * 9))) return rc;
+	std::vector<int32_t> ids((size_t)L);
+	for (int64_t l = 0; l < L; l++) ids[(size_t)l] = (int32_t)l;
+	CUDA_OK(m, cudaMemcpyAsync(w.leaf, ids.data(), (size_t)L * 4, cudaMemcpyHostToDevice, st));
+	CUDA_OK(m, cudaStreamSynchronize(st));
+	m->launches += launch_leaf_centers(dm, (double *)w.q, st);
+	if ((rc = eval_device(m, w, st, true, (const double *)w.q, L, (double *)w.out, dm.D, (int32_t *)w.leaf, (uint8_t *)w.status))) return rc;
+	m->launches += launch_gather_rows(dm, dm.leaf_center_row, L, (double *)w.truth, st);
+	double *de = (double *)w.misc;
+	uint8_t *ds = (uint8_t *)w.misc + L * 8;
+	CUDA_OK(m, cudaMemsetAsync(w.misc, 0, (size_t)L * 9, st));
+	m->launches += launch_error_reduce(dm, (const double *)w.out, (const double *)w.truth, (const int32_t *)w.leaf, (const uint8_t *)w.status, L, threshold, de, ds, nullptr, st);
+	CUDA_OK(m, cudaGetLastError());
+	CUDA_OK(m, cudaMemcpyAsync(err_max, de, (size_t)L * 8, cudaMemcpyDeviceToHost, st));
+	CUDA_OK(m, cudaMemcpyAsync(split, ds, (size_t)L, cudaMemcpyDeviceToHost, st));
+	CUDA_OK(m, cudaStreamSynchronize(st));
+	return LOCO_OK;
+}
+
+int loco_error_check_generated_device(loco_model_t *m, int64_t ppl, uint64_t seed, const double *amp, const double *phase, int32_t n_terms,
+                                      double threshold, double *err_max, uint8_t *split, void *cuda_stream)
+{
+	if (!m || !err_max || !split || !amp || !phase || ppl < 1 || n_terms < 0) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (m->dm.D != 1) return fail(m, LOCO_ERR_INVALID, "generated error check needs a scalar function");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	Workspace &w = m->ws[0];
+	CUDA_OK(m, cudaMemsetAsync(err_max, 0, (size_t)dm.L * 8, st));
+	CUDA_OK(m, cudaMemsetAsync(split, 0, (size_t)dm.L, st));
+	const int64_t total = (int64_t)dm.L * ppl;
+	const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);
+	int rc;
+	if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
+	if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * 8))) return rc;
+	if ((rc = grow(m, &w.truth, &w.truth_b, (size_t)chunk * 8))) return rc;
+	if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
+	if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
+	for (int64_t o = 0; o < total; o += chunk) {
+		const int64_t n = std::min(chunk, total - o);
+		m->launches += launch_jitter_points(dm, ppl, seed, o, n, amp, phase, n_terms, (double *)w.q, (int32_t *)w.leaf, (double *)w.truth, st);
+		if ((rc = eval_device(m, w, st, true, (const double *)w.q, n, (double *)w.out, 1, (int32_t *)w.leaf, (uint8_t *)w.status))) return rc;
+		m->launches += launch_error_reduce(dm, (const double *)w.out, (const double *)w.truth, (const int32_t *)w.leaf, (const uint8_t *)w.status, n, threshold,
+		                                   err_max, split, nullptr, st);
+	}
+	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+// ---- options ---------------------------------------------------------------------------------------------------
+int loco_set_option(loco_model_t *m, const char *name, int64_t value)
+{
+	if (!m || !name) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (!strcmp(name, "path")) { m->opt_path = value; return LOCO_OK; }
+	if (!strcmp(name, "fp32")) { m->opt_fp32 = value; return LOCO_OK; }
+	return fail(m, LOCO_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int64_t loco_kernel_launches(const loco_model_t *m) { return m ? m->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,60 @@
+// loco_device.h -- device image of the flat model and the kernel launch interface.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "loco_flat.h"
+
+namespace loco {
+
+// Pointers into HBM; passed by value to every kernel.  Layout documented in DESIGN.md ("HBM layout").
+struct DeviceModel {
+	int32_t N, D, basis, exact_rcp;
+	int32_t L, C, max_support, max_terms;
+	int64_t R, value_stride;          // rows and row stride (doubles) of the value table
+	const double *dom_min, *dom_max;  // [N]
+	const TreeCell *cells;            // [C] pre-order k-d tree, 16 B per cell
+	const double *leaf_lo_eps, *leaf_hi_eps;  // [L*N]
+	const double *leaf_lo, *leaf_hi;          // [L*N]
+	const uint8_t *leaf_status;       // [L]
+	const int32_t *leaf_center_row;   // [L]
+	const int32_t *sup_off;           // [L+1]
+	const int32_t *sup_row;           // [sum K]
+	const int32_t *term_off;          // [L+1]
+	const double *term_cs;            // [sum T * 2N]
+	const double *term_w;             // [sum T]
+	const int32_t *term_slot;         // [sum T]
+	const int32_t *term_row;          // [sum T]
+	const double *values;             // [R * value_stride]
+};
+
+const int kMaxTemplateN = 8;   // N = 1..8 get fully unrolled kernels
+const int kMaxN = 16;          // larger N use the runtime-N instantiation (coordinates in local memory)
+
+// ---- launchers (loco_kernels.cu).  All asynchronous on `st`; return the number of kernels launched.
+// fused map -> locate -> weights -> weighted sum for scalar functions (D == 1), one thread per query
+int launch_eval_scalar_direct(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf,
+                              uint8_t *status, cudaStream_t st);
+// same, but q holds CUBE coordinates and leaf[] the cell to evaluate in (evaluation on a known cell)
+int launch_eval_scalar_in_cube(const DeviceModel &m, const double *x, int64_t Q, double *out, int32_t *leaf,
+                               uint8_t *status, cudaStream_t st);
+// locate only: cube coordinates xs [Q*N] (may be null), leaf, status
+int launch_locate(const DeviceModel &m, const double *q, int64_t Q, double *xs, int32_t *leaf, uint8_t *status, cudaStream_t st);
+// per-sample weights of each query's leaf: W [Q * max_support] (slots beyond K are zero)
+int launch_weights(const DeviceModel &m, const double *q, int64_t Q, double *W, int32_t *leaf, uint8_t *status, cudaStream_t st);
+int launch_weights_in_cube(const DeviceModel &m, const double *x, int64_t Q, double *W, int32_t *leaf, uint8_t *status, cudaStream_t st);
+// out[q][:] = sum_k W[q][k] * values[sup_row[leaf][k]][:]
+int launch_mesh_gather(const DeviceModel &m, const double *W, const int32_t *leaf, const uint8_t *status, int64_t Q,
+                       double *out, int64_t out_stride, cudaStream_t st);
+// checksum[q] = sum_j out[q][j] * (1 + j % 7)
+int launch_checksum(const double *out, int64_t out_stride, int32_t D, int64_t Q, double *checksum, cudaStream_t st);
+// error check reduction: per-leaf max |out - truth| and split flag
+int launch_error_reduce(const DeviceModel &m, const double *out, const double *truth, const int32_t *leaf, const uint8_t *status,
+                        int64_t P, double threshold, double *err_max, uint8_t *split, unsigned long long *n_bad, cudaStream_t st);
+int launch_fill_values(double *values, int64_t R, int64_t D, int64_t stride, double seed, cudaStream_t st);
+int launch_leaf_centers(const DeviceModel &m, double *q_out, cudaStream_t st);
+int launch_gather_rows(const DeviceModel &m, const int32_t *rows, int64_t n, double *out, cudaStream_t st);
+int launch_jitter_points(const DeviceModel &m, int64_t points_per_leaf, uint64_t seed, int64_t first, int64_t count,
+                         const double *amp, const double *phase, int32_t n_terms, double *q_out, int32_t *leaf_out,
+                         double *truth_out, cudaStream_t st);
+
+} // namespace loco

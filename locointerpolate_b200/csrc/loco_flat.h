@@ -1,0 +1,74 @@
+// loco_flat.h -- the flattened, GPU-ready model (host image) and the flattener.
+//
+// Everything the reference recomputes per query from its pointer graph
+//   * the leaf's influencing-sample set   (LCAdaptiveGridCell::getAllInfluencingSamples, LCAdaptiveGridCell.cpp:558-607)
+//   * which basis functions can be non-zero on the leaf (LCSample::getInterpolationWeight, LCSample.cpp:76-89)
+//   * the +-EPSILON containment bounds     (LCAdaptiveGridCell::evalPametersAreInCell, :438-454)
+// is a pure function of the leaf and is therefore computed ONCE here, into SoA arrays that are
+// uploaded verbatim.  Numbering is canonical: cells in pre-order, leaf index = rank
+// in getAllLeafCells order (:247-258), sample index = position in samples_.
+#pragma once
+#include "loco_graph.h"
+
+namespace loco {
+
+const double kEpsilon = 0.000001;             // LCMathHelper::EPSILON (LCMathHelper.cpp:84)
+const double kContainingEpsilon = 0.0000001;  // LCAdaptiveGridCell::CONTAINING_EPSILON (LCAdaptiveGridCell.h:109)
+
+// per-query status byte
+enum QueryStatus : uint8_t {
+	ST_OK = 0,
+	ST_OUTSIDE_CELL = 1,      // "parameter ouside cell"                   LCAdaptiveGridCell.cpp:450
+	ST_BAD_ARITY = 2,         // "invalid number of parameters"           LCAdaptiveGridCell.cpp:441-444 (host facade only)
+	ST_NO_COMMON_SAMPLE = 3,  // "could not find closest sample"          LCAdaptiveGridCell.cpp:533-538
+	ST_EMPTY_SUPPORT = 4,     // "cannot create new from empty list ..."  LCFunctionValue.cpp:14-17
+};
+const char *status_string(int code);
+
+// one k-d tree cell as the kernels read it: one 16-byte load per level
+struct alignas(16) TreeCell {
+	double split;   // splitVal_
+	int32_t dim;    // splitDirection_, or -1 for a leaf
+	int32_t right;  // inner: pre-order index of child2 (child1 = index+1);  leaf: leaf index
+};
+
+struct Flat {
+	int32_t N = 0, D = 1, basis = 0;
+	int64_t S = 0;  // samples
+	int64_t R = 0;  // value rows
+	int64_t L = 0;  // leaves
+	int64_t C = 0;  // tree cells
+	int32_t depth = 0;       // deepest leaf level
+	int32_t max_support = 0; // max K over leaves
+	int32_t max_terms = 0;   // max T over leaves
+	bool exact_rcp = false;  // every support is a power of two: term_cs holds 1/s and u=(x-c)*(1/s) is bit-identical to (x-c)/s
+
+	std::vector<double> dom_min, dom_max;  // [N] ranges_[2i], ranges_[2i+1]
+	std::vector<TreeCell> cells;           // [C] pre-order
+	std::vector<double> leaf_lo, leaf_hi;          // [L*N] leaf box
+	std::vector<double> leaf_lo_eps, leaf_hi_eps;  // [L*N] lo-EPSILON, hi+EPSILON as the reference computes them
+	std::vector<int32_t> leaf_center_row;          // [L] value row of centerShapeInfo_ (true f at the centre)
+	std::vector<uint8_t> leaf_status;              // [L] ST_OK, or the error every query in this leaf gets
+
+	// influencing-sample sets, CSR by leaf, sorted by sample index (the "support set" parity object)
+	std::vector<int64_t> sup_off;      // [L+1]
+	std::vector<int32_t> sup_sample;   // [sum K]
+	std::vector<int32_t> sup_row;      // [sum K] value row used for that (leaf,sample) pair
+
+	// terms, CSR by leaf: every basis function of every influencing sample whose box can reach the leaf
+	std::vector<int64_t> term_off;     // [L+1]
+	std::vector<double> term_cs;       // [sum T * 2N]  (c_0, s_0, c_1, s_1, ...) ; s or 1/s, see exact_rcp
+	std::vector<double> term_w;        // [sum T] weight_
+	std::vector<int32_t> term_slot;    // [sum T] position of the owning sample in the leaf's support list (ascending)
+	std::vector<int32_t> term_row;     // [sum T] = sup_row[sup_off[leaf] + slot]
+
+	std::vector<int32_t> sample_row;   // [S]
+	std::vector<double> values;        // [R*D] (may be empty when the table is filled on the device)
+
+	// leaf adjacency kept for introspection / tests
+	std::vector<int32_t> n_leaf_neighbors, n_border_neighbors;  // [L]
+};
+
+Status flatten(const Graph &g, Flat *out);
+
+} // namespace loco

@@ -1,0 +1,255 @@
+// loco_flatten.cpp -- Graph -> Flat.
+//
+// Mirrors what the reference does between loading a file and answering the first query:
+//   * leaf<->leaf neighbours        LCAdaptiveGridCell::addAllNeighboursTopDown (LCAdaptiveGridCell.cpp:139-164)
+//                                   with the box test of checkIsNeighbor (:910-925, tolerance 1e-7)
+//   * border cell<->leaf neighbours LCSampledFunction::addBorderCells (LCSampledFunction.cpp:24-47) through
+//                                   LCAdaptiveGridCell::getAdjacentLeaves (:310-333)
+//   * influencing-sample sets       LCAdaptiveGridCell::getAllInfluencingSamples (:558-607)
+// and then pre-filters each leaf's basis functions to those whose box can reach the leaf (terms that
+// are identically zero on the leaf only ever add +0.0 to LCSample::getInterpolationWeight's sum).
+#include "loco_flat.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace loco {
+
+const char *status_string(int code)
+{
+	switch (code) {
+	case ST_OK: return "no error";
+	case ST_OUTSIDE_CELL: return "parameter ouside cell";  // sic, LCAdaptiveGridCell.cpp:450
+	case ST_BAD_ARITY: return "invalid number of parameters";
+	case ST_NO_COMMON_SAMPLE: return "could not find closest sample";
+	case ST_EMPTY_SUPPORT: return "cannot create new from empty list of weighted samples";
+	default: return "unknown status";
+	}
+}
+
+namespace {
+
+struct Ctx {
+	const Graph &g;
+	Flat &f;
+	int N;
+	std::vector<int32_t> leaf_of_cell;  // pre-order cell -> leaf rank or -1
+	std::vector<int32_t> cell_of_leaf;
+	explicit Ctx(const Graph &g_, Flat &f_) : g(g_), f(f_), N(g_.N) {}
+
+	const double *box(const Graph::CellSet &cs, int64_t i) const { return &cs.ranges[(size_t)i * 2 * N]; }
+
+	// LCAdaptiveGridCell::checkIsNeighbor (LCAdaptiveGridCell.cpp:910-925)
+	bool touches(const double *a, const double *b) const
+	{
+		for (int i = 0; i < N; i++) {
+			double minA = a[2 * i], maxA = a[2 * i + 1], minB = b[2 * i], maxB = b[2 * i + 1];
+			if (((minB - maxA) > kContainingEpsilon) || ((minA - maxB) > kContainingEpsilon)) return false;
+		}
+		return true;
+	}
+
+	// all leaves whose box touches `a` (the fixed point of addAllNeighboursTopDown: a cell only ever
+	// inherits neighbours that touch its parent, so the final lists are exactly the touching leaves)
+	void touching_leaves(int32_t cell, const double *a, int32_t self_leaf, std::vector<int32_t> *out) const
+	{
+		if (!touches(a, box(g.tree, cell))) return;
+		if (g.tree.split_dir[cell] < 0) {
+			if (leaf_of_cell[cell] != self_leaf) out->push_back(leaf_of_cell[cell]);
+			return;
+		}
+		touching_leaves(cell + 1, a, self_leaf, out);
+		touching_leaves(g.tree.child2[cell], a, self_leaf, out);
+	}
+
+	// LCAdaptiveGridCell::evalPametersAreInCell (:438-454)
+	bool in_cell_eps(int32_t cell, const double *x) const
+	{
+		const double *r = box(g.tree, cell);
+		for (int i = 0; i < N; i++)
+			if ((x[i] < r[2 * i] - kEpsilon) || (x[i] > r[2 * i + 1] + kEpsilon)) return false;
+		return true;
+	}
+
+	// LCAdaptiveGridCell::getAdjacentLeaves (:310-333), including its early return on the first leaf
+	// that rejects the point (leaves inserted before that stay in the result)
+	bool adjacent_leaves(int32_t cell, const double *x, std::vector<int32_t> *out) const
+	{
+		int32_t dir = g.tree.split_dir[cell];
+		if (dir < 0) {
+			bool ok = in_cell_eps(cell, x);
+			if (ok) out->push_back(leaf_of_cell[cell]);
+			return ok;
+		}
+		double sv = g.tree.split_val[cell];
+		if (x[dir] <= sv + kContainingEpsilon)
+			if (!adjacent_leaves(cell + 1, x, out)) return false;
+		if (x[dir] >= sv - kContainingEpsilon)
+			if (!adjacent_leaves(g.tree.child2[cell], x, out)) return false;
+		return true;
+	}
+};
+
+bool is_pow2(double s)
+{
+	if (!(s > 0) || !std::isfinite(s)) return false;
+	int e;
+	return std::frexp(s, &e) == 0.5 && std::isnormal(s) && std::isfinite(1.0 / s) && std::isnormal(1.0 / s);
+}
+
+} // namespace
+
+Status flatten(const Graph &g, Flat *out)
+{
+	LOCO_RETURN_IF_ERROR(validate_graph(g));
+	Flat &f = *out;
+	f = Flat();
+	Ctx cx(g, f);
+	const int N = g.N;
+	f.N = N; f.D = g.D; f.basis = g.basis;
+	f.S = g.n_samples(); f.R = g.n_rows(); f.C = g.tree.size();
+	for (int i = 0; i < N; i++) { f.dom_min.push_back(g.domain[2 * i]); f.dom_max.push_back(g.domain[2 * i + 1]); }
+
+	// ---- tree cells, leaf numbering (getAllLeafCells order == pre-order rank of leaves) -----------
+	f.cells.resize((size_t)f.C);
+	cx.leaf_of_cell.assign((size_t)f.C, -1);
+	std::vector<int32_t> level((size_t)f.C, 0);
+	for (int64_t c = 0; c < f.C; c++) {
+		TreeCell &tc = f.cells[(size_t)c];
+		tc.dim = g.tree.split_dir[c];
+		tc.split = g.tree.split_val[c];
+		if (tc.dim < 0) {
+			tc.right = (int32_t)cx.cell_of_leaf.size();
+			cx.leaf_of_cell[(size_t)c] = tc.right;
+			cx.cell_of_leaf.push_back((int32_t)c);
+			f.depth = std::max(f.depth, level[(size_t)c]);
+		} else {
+			tc.right = g.tree.child2[c];
+			level[(size_t)c + 1] = level[(size_t)c] + 1;
+			level[(size_t)tc.right] = level[(size_t)c] + 1;
+		}
+	}
+	f.L = (int64_t)cx.cell_of_leaf.size();
+	const int64_t L = f.L;
+	f.leaf_lo.resize((size_t)L * N); f.leaf_hi.resize((size_t)L * N);
+	f.leaf_lo_eps.resize((size_t)L * N); f.leaf_hi_eps.resize((size_t)L * N);
+	f.leaf_center_row.resize((size_t)L);
+	f.leaf_status.assign((size_t)L, ST_OK);
+	for (int64_t l = 0; l < L; l++) {
+		const double *r = cx.box(g.tree, cx.cell_of_leaf[(size_t)l]);
+		for (int i = 0; i < N; i++) {
+			f.leaf_lo[(size_t)l * N + i] = r[2 * i];
+			f.leaf_hi[(size_t)l * N + i] = r[2 * i + 1];
+			f.leaf_lo_eps[(size_t)l * N + i] = r[2 * i] - kEpsilon;      // same double op as :447
+			f.leaf_hi_eps[(size_t)l * N + i] = r[2 * i + 1] + kEpsilon;  // same double op as :448
+		}
+		f.leaf_center_row[(size_t)l] = g.tree.center_row[cx.cell_of_leaf[(size_t)l]];
+	}
+
+	// ---- neighbours ---------------------------------------------------------------------------------
+	const bool cubic = g.basis == CUBIC_BSPLINE;
+	std::vector<std::vector<int32_t>> leaf_nb((size_t)L), border_nb((size_t)L);
+	// the neighbour relation exists for both basis types (split()/addAllNeighboursTopDown maintain it
+	// regardless); only the cubic influencing set consumes it
+	for (int64_t l = 0; l < L; l++) {
+		cx.touching_leaves(0, cx.box(g.tree, cx.cell_of_leaf[(size_t)l]), (int32_t)l, &leaf_nb[(size_t)l]);
+		std::sort(leaf_nb[(size_t)l].begin(), leaf_nb[(size_t)l].end());
+	}
+	{
+		// addBorderCells: every leaf adjacent to any sample centre of the border cell
+		std::vector<int32_t> stamp((size_t)L, -1), found;
+		for (int64_t b = 0; b < g.border.size(); b++) {
+			found.clear();
+			for (int64_t e = g.border.ls_off[b]; e < g.border.ls_off[b + 1]; e++)
+				cx.adjacent_leaves(0, &g.sample_center[(size_t)g.border.ls_sample[e] * N], &found);
+			for (int32_t l : found) {
+				if (stamp[(size_t)l] == (int32_t)b) continue;
+				stamp[(size_t)l] = (int32_t)b;
+				border_nb[(size_t)l].push_back((int32_t)b);
+			}
+		}
+	}
+	f.n_leaf_neighbors.resize((size_t)L); f.n_border_neighbors.resize((size_t)L);
+	for (int64_t l = 0; l < L; l++) {
+		f.n_leaf_neighbors[(size_t)l] = (int32_t)leaf_nb[(size_t)l].size();
+		f.n_border_neighbors[(size_t)l] = (int32_t)border_nb[(size_t)l].size();
+	}
+
+	// ---- influencing-sample sets (getAllInfluencingSamples) -----------------------------------------------
+	f.sup_off.assign(1, 0);
+	std::vector<int64_t> seen((size_t)f.S, -1), own((size_t)f.S, -1);
+	std::vector<std::pair<int32_t, int32_t>> sup;  // (sample, row)
+	for (int64_t l = 0; l < L; l++) {
+		sup.clear();
+		int32_t cell = cx.cell_of_leaf[(size_t)l];
+		for (int64_t e = g.tree.ls_off[cell]; e < g.tree.ls_off[cell + 1]; e++) {
+			int32_t s = g.tree.ls_sample[e];
+			if (seen[(size_t)s] == l) continue;
+			seen[(size_t)s] = l; own[(size_t)s] = l;
+			sup.push_back({s, g.tree.ls_row[e]});
+		}
+		if (cubic) {
+			auto take = [&](const Graph::CellSet &cs, int32_t nb) {
+				bool checked = false;
+				for (int64_t e = cs.ls_off[nb]; e < cs.ls_off[nb + 1]; e++) {
+					int32_t s = cs.ls_sample[e];
+					if (seen[(size_t)s] == l) continue;
+					if (!checked) {
+						// getNeightbourShapeInfoMappingMapping (:507-556) needs a sample common to both cells
+						bool common = false;
+						for (int64_t e2 = cs.ls_off[nb]; e2 < cs.ls_off[nb + 1] && !common; e2++) common = own[(size_t)cs.ls_sample[e2]] == l;
+						if (!common) f.leaf_status[(size_t)l] = ST_NO_COMMON_SAMPLE;
+						checked = true;
+					}
+					seen[(size_t)s] = l;
+					sup.push_back({s, cs.ls_row[e]});
+				}
+			};
+			for (int32_t nb : leaf_nb[(size_t)l]) take(g.tree, cx.cell_of_leaf[(size_t)nb]);
+			for (int32_t nb : border_nb[(size_t)l]) take(g.border, nb);
+		}
+		if (sup.empty() && f.leaf_status[(size_t)l] == ST_OK) f.leaf_status[(size_t)l] = ST_EMPTY_SUPPORT;
+		std::sort(sup.begin(), sup.end());
+		for (auto &p : sup) { f.sup_sample.push_back(p.first); f.sup_row.push_back(p.second); }
+		f.sup_off.push_back((int64_t)f.sup_sample.size());
+		f.max_support = std::max<int32_t>(f.max_support, (int32_t)sup.size());
+	}
+
+	// ---- terms ------------------------------------------------------------------------------------------
+	f.exact_rcp = true;
+	for (double s : g.bf_support) if (!is_pow2(s)) { f.exact_rcp = false; break; }
+	f.term_off.assign(1, 0);
+	for (int64_t l = 0; l < L; l++) {
+		const double *lo = &f.leaf_lo_eps[(size_t)l * N], *hi = &f.leaf_hi_eps[(size_t)l * N];
+		for (int64_t k = f.sup_off[(size_t)l]; k < f.sup_off[(size_t)l + 1]; k++) {
+			int32_t s = f.sup_sample[(size_t)k];
+			for (int64_t b = g.bf_off[s]; b < g.bf_off[s + 1]; b++) {
+				const double *c = &g.bf_center[(size_t)b * N], *sp = &g.bf_support[(size_t)b * N];
+				bool reach = true;
+				for (int i = 0; i < N && reach; i++) {
+					// keep unless the basis box is provably disjoint from every accepted point of the leaf
+					// ([lo-EPS, hi+EPS]); the margin only ever keeps extra (zero) terms
+					double m = 1e-9 + 1e-12 * (std::fabs(c[i]) + std::fabs(sp[i]) + std::fabs(lo[i]) + std::fabs(hi[i]));
+					if ((c[i] + sp[i] < lo[i] - m) || (c[i] - sp[i] > hi[i] + m)) reach = false;
+				}
+				if (!reach) continue;
+				for (int i = 0; i < N; i++) {
+					f.term_cs.push_back(c[i]);
+					f.term_cs.push_back(f.exact_rcp ? 1.0 / sp[i] : sp[i]);
+				}
+				f.term_w.push_back(g.bf_weight[b]);
+				f.term_slot.push_back((int32_t)(k - f.sup_off[(size_t)l]));
+				f.term_row.push_back(f.sup_row[(size_t)k]);
+			}
+		}
+		f.term_off.push_back((int64_t)f.term_w.size());
+		f.max_terms = std::max<int32_t>(f.max_terms, (int32_t)(f.term_off[(size_t)l + 1] - f.term_off[(size_t)l]));
+	}
+
+	f.sample_row = g.sample_row;
+	f.values = g.values;
+	return Status();
+}
+
+} // namespace loco

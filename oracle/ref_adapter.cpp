@@ -38,6 +38,8 @@
 #include "LCAdaptiveGrid.h"
 #include "LCSampledFunction.h"
 
+#include "../include/loco_b200.h"  // only the plain-array graph description loco_graph_t
+
 namespace {
 
 // The reference prints diagnostics on std::cout from inside the hot path (e.g. the
@@ -237,6 +239,70 @@ void *ref_fn_reload(void *fp)
 	for (LCAdaptiveGridCell *b : r->border) border.push_back(reloadCell(b, nullptr, 0, map));
 	std::vector<double> ranges;
 	r->fn->getRanges(&ranges);
+	LCSampledFunction *fn = new LCSampledFunction(root, ranges, samples, border);
+	fn->addBorderCells();
+	return wrap(fn);
+}
+
+// Build REFERENCE objects from a plain-array graph through the loader's code path (the same constructor
+// sequence as convertToCplusplus, LCProtoConverter.cpp:356-403).  This is how bench.py hands the
+// benchmark model to the reference for the CPU baseline without paying the reference's O(n^2) builder
+// (87 s for the 43k-sample config).  Scalar values only (the reference has no other kind).
+static LCAdaptiveGridCell *cellFromGraph(const loco_graph_t *g, int64_t *next, LCAdaptiveGridCell *parent, int level,
+                                         std::vector<LCSample *> &samples)
+{
+	int64_t i = (*next)++;
+	int N = g->n_params;
+	std::vector<double> ranges(g->cell_ranges + i * 2 * N, g->cell_ranges + (i + 1) * 2 * N);
+	if (g->cell_split_dir[i] < 0) {
+		std::unordered_map<LCSample *, LCFunctionValue *> leafSamples;
+		for (int64_t e = g->cell_sample_offset[i]; e < g->cell_sample_offset[i + 1]; e++) {
+			int s = g->cell_sample[e];
+			leafSamples[samples[s]] = new LCRealFunctionValue(g->cell_sample_value ? g->cell_sample_value[e] : g->sample_value[s]);
+		}
+		LCFunctionValue *center = new LCRealFunctionValue(g->cell_center_value ? g->cell_center_value[i] : 0.0);
+		return new LCAdaptiveGridCell(level, parent, ranges, center, leafSamples);
+	}
+	LCAdaptiveGridCell *cell = new LCAdaptiveGridCell(level, parent, ranges, g->cell_split_dir[i], g->cell_split_val[i]);
+	LCAdaptiveGridCell *c1 = cellFromGraph(g, next, cell, level + 1, samples);
+	LCAdaptiveGridCell *c2 = cellFromGraph(g, next, cell, level + 1, samples);
+	cell->setChildren(c1, c2);
+	return cell;
+}
+
+void *ref_fn_from_graph(const loco_graph_t *g)
+{
+	CoutMute mute;
+	if (g->value_dim != 1) return nullptr;
+	int N = g->n_params;
+	std::vector<LCSample *> samples;
+	for (int64_t s = 0; s < g->n_samples; s++) {
+		Eigen::VectorXd center(N);
+		for (int d = 0; d < N; d++) center(d) = g->sample_center[s * N + d];
+		std::vector<LCBasisFunction *> bfs;
+		for (int64_t b = g->bf_offset[s]; b < g->bf_offset[s + 1]; b++) {
+			Eigen::VectorXd c(N), sp(N);
+			for (int d = 0; d < N; d++) { c(d) = g->bf_center[b * N + d]; sp(d) = g->bf_support[b * N + d]; }
+			if (g->basis_type == 0) bfs.push_back(new LCLinearBSpline(c, sp, g->bf_weight[b]));
+			else bfs.push_back(new LCCubicBSpline(c, sp, g->bf_weight[b]));
+		}
+		samples.push_back(new LCSample(center, bfs, new LCRealFunctionValue(g->sample_value[s])));
+	}
+	int64_t next = 0;
+	LCAdaptiveGridCell *root = cellFromGraph(g, &next, nullptr, 0, samples);
+	root->addAllNeighboursTopDown();
+	std::vector<LCAdaptiveGridCell *> border;
+	for (int64_t b = 0; b < g->n_border_cells; b++) {
+		std::vector<double> ranges(g->border_ranges + b * 2 * N, g->border_ranges + (b + 1) * 2 * N);
+		std::unordered_map<LCSample *, LCFunctionValue *> cellSamples;
+		for (int64_t e = g->border_sample_offset[b]; e < g->border_sample_offset[b + 1]; e++) {
+			int s = g->border_sample[e];
+			cellSamples[samples[s]] = new LCRealFunctionValue(g->border_sample_value ? g->border_sample_value[e] : g->sample_value[s]);
+		}
+		LCFunctionValue *center = new LCRealFunctionValue(g->border_center_value ? g->border_center_value[b] : 0.0);
+		border.push_back(new LCAdaptiveGridCell(0, nullptr, ranges, center, cellSamples));
+	}
+	std::vector<double> ranges(g->domain, g->domain + 2 * N);
 	LCSampledFunction *fn = new LCSampledFunction(root, ranges, samples, border);
 	fn->addBorderCells();
 	return wrap(fn);

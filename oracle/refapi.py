@@ -39,6 +39,8 @@ def lib():
         L.ref_grid_true_values.argtypes = [vp, vp, l, vp]
         L.ref_fn_from_grid.restype = vp
         L.ref_fn_from_grid.argtypes = [vp]
+        L.ref_fn_from_graph.restype = vp
+        L.ref_fn_from_graph.argtypes = [vp]
         L.ref_fn_reload.restype = vp
         L.ref_fn_reload.argtypes = [vp]
         L.ref_fn_sizes.argtypes = [vp, vp]
@@ -133,6 +135,15 @@ class RefFn:
         s = np.zeros(9, dtype=np.int64)
         lib().ref_fn_sizes(h, _p(s))
         (self.N, self.S, self.C, self.L, self.Bc, self.B, self.E, self.Eb, self.basis) = (int(x) for x in s)
+
+    @classmethod
+    def from_graph(cls, g):
+        """Reference objects built from a GraphArrays through the loader's constructor sequence."""
+        s = g.struct()
+        h = lib().ref_fn_from_graph(C.byref(s))
+        if not h:
+            raise RuntimeError("the reference only has scalar (LCRealFunctionValue) values")
+        return cls(h)
 
     def reload(self):
         """Rebuild through the loader's code path (LCProtoConverter.cpp:356-403 without protobuf)."""

@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: committed golden vectors produced by the
+reference's own code, the CPU restatement in oracle/, and size-independent properties at larger sizes.
+
+Bars (BASELINE.json north_star): leaf indices, status bytes and support sets bit-exact; fp64 values within
+1e-12 relative (see conftest.VALUE_RTOL for what "relative" is taken against)."""
+import numpy as np
+import pytest
+
+import protoschema
+from conftest import GOLDEN_CASES, assert_values_close
+from locointerpolate_b200 import capi
+from oracle import oracleapi
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_vectors(golden, name, path):
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    m.set_option("path", path)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    out, leaf, status = m.eval(z["q"])
+    assert m.kernel_launches > 0
+    assert np.array_equal(leaf, z["leaf"]), "containing leaf differs from the reference"
+    assert np.array_equal(status, z["status"])
+    ok = status == 0
+    o_out, _, _, scale = orc.eval(z["q"])
+    assert_values_close(out[ok], z["out"][ok], scale[ok])   # vs the reference's own output
+    assert_values_close(out[ok], o_out[ok], scale[ok])      # vs the CPU restatement
+    assert np.isnan(out[~ok]).all()
+    for l in range(m.L):
+        assert np.array_equal(m.support_set(l), z["sup_ids"][z["sup_off"][l]:z["sup_off"][l + 1]])
+    err, split = m.center_error(0.05)
+    assert np.allclose(err, z["center_err"], rtol=0, atol=1e-13)
+    assert np.array_equal(split.astype(bool), ~((z["center_err"] - 0.05) <= 0))
+
+
+@pytest.mark.parametrize("name", ["c1_lin2d_boot2", "cub2d_adapt6", "cub3d_boot2"])
+def test_device_buffers_and_ragged_sizes(golden, name):
+    torch = _torch()
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    rng = np.random.default_rng(5)
+    for Q in (0, 1, 31, 257, 4099):
+        q = rng.random((Q, m.N))
+        tq = torch.from_numpy(q).cuda()
+        out = torch.empty(Q, dtype=torch.float64, device="cuda")
+        leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+        status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        m.eval_device(tq.data_ptr(), Q, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
+        torch.cuda.synchronize()
+        o_out, o_leaf, o_status, scale = orc.eval(q)
+        assert np.array_equal(leaf.cpu().numpy(), o_leaf) and np.array_equal(status.cpu().numpy(), o_status)
+        assert_values_close(out.cpu().numpy(), o_out, scale)
+        # leaf / status outputs are optional
+        out2 = torch.empty_like(out)
+        m.eval_device(tq.data_ptr(), Q, out2.data_ptr(), 0, 0, stream)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("name,D", [("c1_lin2d_boot2", 6), ("cub2d_adapt6", 7), ("cub3d_boot2", 30), ("lin4d_boot1", 300)])
+def test_mesh_valued(golden, name, D):
+    """D > 1: per-vertex mesh vectors.  Oracle = LCRealFunctionValue::add applied component-wise."""
+    pb, z = golden(name)
+    g = protoschema.read_binary(pb)
+    rng = np.random.default_rng(11)
+    g.D = D
+    g.sample_value = rng.standard_normal((len(g.sample_center), D))
+    g.cell_sample_value = g.border_sample_value = g.cell_center_value = g.border_center_value = None
+    g.normalise()
+    m = capi.Model.from_graph(g, device=0)
+    orc = oracleapi.Oracle(g)
+    q = z["q"][:400]
+    out, leaf, status = m.eval(q)
+    o_out, o_leaf, o_status, scale = orc.eval(q)
+    assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
+    ok = status == 0
+    assert_values_close(out[ok], o_out[ok], scale[ok])
+    assert np.isnan(out[~ok]).all()
+
+
+def test_error_check_matches_oracle(golden):
+    pb, z = golden("cub2d_adapt6")
+    m = capi.Model.from_proto(pb, device=0)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    q, truth = z["q"], z["true_values"]
+    for thr in (0.01, 0.1):
+        err, split, bad = m.error_check(q, truth, thr)
+        o_err, o_split, o_bad = orc.error_check(q, truth, thr)
+        assert bad == o_bad == 16
+        assert np.allclose(err, o_err, rtol=0, atol=1e-12)
+        flips = split != o_split  # a flag may only differ where the error sits within rounding of the threshold
+        assert (np.abs(o_err[flips] - thr) < 1e-12).all()
+    # NaN truth => split (decideSplit is written as !(max(diff - allowed) <= 0))
+    truth2 = truth.copy()
+    truth2[200] = np.nan
+    err, split, _ = m.error_check(q, truth2, 10.0)
+    _, leaf, _, _ = orc.eval(q[200:201])
+    assert split[leaf[0]] == 1 and split.sum() == 1 and np.isnan(err[leaf[0]])
+
+
+@pytest.mark.parametrize("N,basis,level", [(3, capi.CUBIC, 3), (4, capi.LINEAR, 2), (6, capi.LINEAR, 1), (2, capi.CUBIC, 5)])
+def test_bootstrap_models_against_oracle(N, basis, level, tmp_path):
+    def f(p):
+        return 1 + np.sin(3 * p + np.arange(len(p))).sum()
+    m = capi.Model.bootstrap(N, basis, level, 1, True, fn=f, device=0)
+    path = str(tmp_path / "m.pb")
+    m.save_proto(path)
+    orc = oracleapi.Oracle(protoschema.read_binary(path))
+    q = np.random.default_rng(2).random((3000, N)) * 1.000002 - 0.000001
+    out, leaf, status = m.eval(q)
+    o_out, o_leaf, o_status, scale = orc.eval(q)
+    assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
+    assert_values_close(out, o_out, scale)
+
+
+@pytest.mark.parametrize("N,basis,level,Q", [(3, capi.CUBIC, 5, 4_000_000), (4, capi.LINEAR, 3, 2_000_000), (6, capi.CUBIC, 1, 200_000),
+                                             (8, capi.LINEAR, 1, 500_000)])
+def test_full_size_properties(N, basis, level, Q):
+    """BASELINE-size trees, checked through properties that need no oracle run:
+    linear precision (f = 1 + sum (i+1) x_i is reproduced; TestExamples.cpp:313-448) and partition of
+    unity (LCAdaptiveGridCell.cpp:655) -- both to 1e-12 instead of the reference's 1e-5 / 1e-6."""
+    torch = _torch()
+    coef = np.arange(1, N + 1, dtype=np.float64)
+    m = capi.Model.bootstrap(N, basis, level, 1, True, fn=lambda p: 1 + (coef * p).sum(), device=0)
+    tq = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    out = torch.empty(Q, dtype=torch.float64, device="cuda")
+    leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+    status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+    m.eval_device(tq.data_ptr(), Q, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(status.sum()) == 0
+    exact = 1 + (tq * torch.from_numpy(coef).cuda()).sum(dim=1)
+    assert float((out - exact).abs().max()) < 1e-12 * (1 + coef.sum())
+    assert int(leaf.min()) == 0 and int(leaf.max()) == m.L - 1   # every leaf is hit, indices in range
+    m.set_values(np.ones((m.info["n_value_rows"], 1)))
+    m.eval_device(tq.data_ptr(), Q, out.data_ptr(), 0, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((out - 1).abs().max()) < 1e-12
+
+
+def test_mesh_ring_checksum():
+    """Mesh batches too large to keep are streamed through a ring; the per-query checksum must equal the
+    checksum of the directly evaluated result."""
+    torch = _torch()
+    N, D, Q = 4, 3000, 1000
+    m = capi.Model.bootstrap(N, capi.LINEAR, 2, D, True, device=0)
+    m.fill_values_synthetic(0.25)
+    tq = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    out = torch.empty((Q, D), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    m.eval_device(tq.data_ptr(), Q, out.data_ptr(), 0, 0, st)
+    ring = torch.empty((128, D), dtype=torch.float64, device="cuda")
+    chk = torch.empty(Q, dtype=torch.float64, device="cuda")
+    m.eval_ring_device(tq.data_ptr(), Q, ring.data_ptr(), 128, chk.data_ptr(), 0, 0, st)
+    torch.cuda.synchronize()
+    wts = (1 + torch.arange(D, device="cuda") % 7).double()
+    ref = (out * wts).sum(dim=1)
+    assert float(((chk - ref).abs() / ref.abs().clamp_min(1)).max()) < 1e-12
+    # the synthetic table is what the header says it is
+    v = m.get_values(5, 2)
+    j = np.arange(D)
+    assert np.allclose(v[0], np.sin(0.37 * j + 0.61 * 5 + 0.25) + 0.001 * (j % 97), atol=1e-12)
