@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched LCSampledFunction evaluation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic queries (per GPU; weak scaling: the batch
+per GPU is fixed as N grows, the model is replicated, queries are independent).  Rank 0 prints ONE JSON line.
+
+Workloads = BASELINE.json configs.  Default c2 (configs[1]): 3-D cubic scalar function,
+bootstrap level 5 -> 32,768 leaves / 42,875 samples / K=64, 100M queries per step.
+
+  value      queries/s with the batch already resident in HBM, timed with CUDA events on the launching stream
+  e2e        the same metric through the host-buffer C-ABI call loco_eval_batch (pinned host memory,
+             H2D + kernels + D2H inside the timed region)
+  roofline   dominant kernel: algorithmic bytes (SURVEY.md 8d formula) / its CUDA-event duration, against
+             the measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own C++ path (oracle/_ref/liblocoref.so, fork-parallel over the host cores)
+             or, where that library is absent, the oracle port, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, basis, bootstrap level, D (doubles per value), eval_corners, queries per step per GPU, description
+    "c1": dict(N=2, basis=0, level=2, D=1, corners=True, Q=1_000_000,
+               desc="2-D linear scalar, TestExamples tree (16 leaves, 25 samples, K=4), 1M queries"),
+    "c2": dict(N=3, basis=1, level=5, D=1, corners=True, Q=100_000_000,
+               desc="3-D cubic scalar, bootstrap 5 (32,768 leaves, 42,875 samples, K=64), 100M queries"),
+    "c3": dict(N=4, basis=0, level=3, D=30_000, corners=True, Q=16_384,
+               desc="4-D linear mesh-valued (10k vertices, D=30,000), bootstrap 3 (4,096 leaves, K=16); 10M queries streamed in 16,384-query batches"),
+    "c4": dict(N=6, basis=1, level=1, D=150_000, corners=False, Q=4_096,
+               desc="6-D cubic mesh-valued (50k vertices, D=150,000), bootstrap 1 (64 leaves, K=4,096); 10M queries streamed in 4,096-query batches"),
+    "c5": dict(N=8, basis=0, level=1, D=1, corners=True, Q=64_000_000,
+               desc="8-D linear scalar error check, bootstrap 1 (256 leaves, K=256); 1B candidate points per pass in 64M-point batches"),
+}
+
+
+def algorithmic_bytes_per_query(N, depth, T, K, D):
+    """a cache-less single pass of the reference's data flow, counted once."""
+    return 8 * N + 16 * depth + T * (16 * N + 8 + 4) + K * D * 8 + 8 * D + 5
+
+
+def test_function(N):
+    """deterministic stand-in for LCRealFunction(N, linear=false) (LCRealFunction.cpp:50-63): 1 + sum_i sum_j a_ij sin(3 j x_i + p_ij)"""
+    rng = np.random.default_rng(5)
+    amp = rng.uniform(-1, 1, (N, 10))
+    phase = rng.uniform(-1, 1, (N, 10))
+    j = np.arange(10)
+
+    def f(p):
+        return 1.0 + float((amp * np.sin(3 * j[None, :] * p[:, None] + phase)).sum())
+    return f, amp, phase
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_model(capi, w, device):
+    f, amp, phase = test_function(w["N"])
+    if w["D"] == 1:
+        m = capi.Model.bootstrap(w["N"], w["basis"], w["level"], 1, w["corners"], fn=f, device=device)
+    else:
+        m = capi.Model.bootstrap(w["N"], w["basis"], w["level"], w["D"], w["corners"], fn=None, device=device)
+        if device >= 0:
+            m.fill_values_synthetic(0.5)
+    return m, amp, phase
+
+
+def cpu_reference_arm(w, sample_q, steps, warmup, name):
+    """The reference's own CPU implementation on the host cores (oracle/_ref when present, else the oracle port)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from locointerpolate_b200 import capi
+    from oracle import oracleapi, refapi
+    import protoschema
+    import tempfile
+    cores = len(os.sched_getaffinity(0))
+    N, D = w["N"], w["D"]
+    wl = dict(w)
+    if D > 1:
+        # the reference has no mesh-valued implementation (LCFunctionValue.cpp:20-31): CPU side = reference weights +
+        # a plain r[j] += w*v[j] loop; the port does exactly that, on a reduced D to bound memory
+        wl["D"] = min(D, 3000)
+    m, _, _ = build_model(capi, {**wl, "D": 1} if D == 1 else wl, capi.HOST_ONLY)
+    kind = "port"
+    rng = np.random.default_rng(99)
+    q = rng.random((sample_q, N))
+    if D == 1 and refapi.available():
+        tmp = tempfile.mktemp(suffix=".pb")
+        m.save_proto(tmp)
+        g = protoschema.read_binary(tmp)
+        os.unlink(tmp)
+        fn = refapi.RefFn.from_graph(g)
+        kind = "reference"
+        run = lambda: fn.eval_fork(q, cores)
+        used = cores
+    else:
+        if D == 1:
+            tmp = tempfile.mktemp(suffix=".pb")
+            m.save_proto(tmp)
+            g = protoschema.read_binary(tmp)
+            os.unlink(tmp)
+        else:
+            g = None
+        if g is None:
+            raise SystemExit("mesh-valued CPU baseline needs a host value table; use --workload c1/c2/c5 for --impl reference")
+        orc = oracleapi.Oracle(g)
+        run = lambda: orc.eval(q)
+        used = 1
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=sample_q / dt, unit="queries/s", cores=used, kind=kind,
+                sample=f"{sample_q} uniform queries of workload {name} per step, {steps} steps, fork-parallel over {used} host cores"
+                if kind == "reference" else f"{sample_q} uniform queries of workload {name} per step, single thread"), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries", type=int, default=0, help="queries per step per GPU (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted tiles")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.queries:
+        w["Q"] = args.queries
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "interpolated_queries_per_sec"
+    config = {"workload": f"{args.workload}: {w['desc']}", "n_params": w["N"], "basis": "cubic" if w["basis"] else "linear",
+              "value_dim": w["D"], "queries_per_step_per_gpu": w["Q"], "parallelism": f"query-sharded x{world}, model replicated",
+              "l2": "inputs+outputs per step exceed the 126 MB L2" if w["Q"] * (w["N"] + w["D"]) * 8 > 126e6 else "L2 flushed between steps"}
+
+    # ------------------------------------------------------------------ reference arm (CPU) ----------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[args.workload]
+        base, dt = cpu_reference_arm(w, args.cpu_sample or cpu_default, max(args.steps, 1), args.warmup, args.workload)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": "queries/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+                          "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU) -----------------
+    import torch
+    import torch.distributed as dist
+    from locointerpolate_b200 import build as product_build, capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if local == 0:
+        product_build.build()
+    if world > 1:
+        dist.barrier()
+    m, amp, phase = build_model(capi, w, local)
+    m.set_option("path", args.path)
+    info = m.info
+    N, D, Q = w["N"], w["D"], w["Q"]
+    gen = torch.Generator("cuda").manual_seed(1234 + rank)
+    q = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=gen)
+    stream = torch.cuda.current_stream().cuda_stream
+    leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+    status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+    flush = None
+    if Q * (N + D) * 8 <= 126e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    if args.workload == "c5":
+        err = torch.empty(info["n_leaves"], dtype=torch.float64, device="cuda")
+        split = torch.empty(info["n_leaves"], dtype=torch.uint8, device="cuda")
+        d_amp, d_phase = torch.from_numpy(amp).cuda(), torch.from_numpy(phase).cuda()
+        ppl = Q // info["n_leaves"]
+        Q = ppl * info["n_leaves"]
+
+        def step(i):
+            m.error_check_generated_device(ppl, 1000 + i, d_amp.data_ptr(), d_phase.data_ptr(), 10, 0.05, err.data_ptr(), split.data_ptr(), stream)
+        out_bytes = info["n_leaves"] * 9
+    elif D == 1:
+        outs = [torch.empty(Q, dtype=torch.float64, device="cuda") for _ in range(2)]
+
+        def step(i):
+            m.eval_device(q.data_ptr(), Q, outs[i % 2].data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
+        out_bytes = Q * 13
+    else:
+        ring_q = min(Q, max(1, (6 << 30) // (D * 8)))
+        ring = torch.empty((ring_q, info["value_dim"] + (info["value_dim"] & 1)), dtype=torch.float64, device="cuda")
+        chk = torch.empty(Q, dtype=torch.float64, device="cuda")
+
+        def step(i):
+            m.eval_ring_device(q.data_ptr(), Q, ring.data_ptr(), ring_q, chk.data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
+        out_bytes = Q * 13
+
+    gathered, handles = None, []
+    if world > 1 and D == 1 and args.workload != "c5":
+        gathered = [torch.empty(world * Q, dtype=torch.float64, device="cuda") for _ in range(2)]
+
+    def run(i):
+        if flush is not None:
+            flush.zero_()
+        step(i)
+        if gathered is not None:  # the path's one exchange step: gather the per-shard results (overlaps the next step)
+            ev = torch.cuda.Event()
+            ev.record()
+            handles.append(dist.all_gather_into_tensor(gathered[i % 2], outs[i % 2], async_op=True))
+
+    for i in range(args.warmup):
+        run(i)
+    for h in handles:
+        h.wait()
+    handles.clear()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = m.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_wall = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run(i)
+    for h in handles:
+        h.wait()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if flush is not None:  # subtract nothing: the flush is inside the timed region and is charged to us
+        pass
+    launches = m.kernel_launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * Q / (ms_per_step * 1e-3)
+    bad = int((status != 0).sum().item()) if args.workload != "c5" else 0
+
+    # ---- dominant kernel alone (no flush, no gather), CUDA events on the launching stream
+    ks = []
+    for i in range(max(3, args.steps)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(i); b.record(); torch.cuda.synchronize()
+        ks.append(a.elapsed_time(b))
+    kernel_ms = float(np.median(ks))
+    T = info["n_terms"] / info["n_leaves"]
+    K = info["n_support_entries"] / info["n_leaves"]
+    algo = algorithmic_bytes_per_query(N, info["depth"], T, K, D) * Q
+    compulsory = Q * (8 * N + 8 * D + 5) + info["device_bytes"]
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": algo / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_query": algo / Q,
+                "compulsory": {"bytes_per_step": compulsory, "achieved_gbs": compulsory / (kernel_ms * 1e-3) / 1e9,
+                               "frac": compulsory / (kernel_ms * 1e-3) / 1e9 / peak},
+                "note": "algorithmic bytes count the reference's per-query data flow without caches (SURVEY.md 8d); terms and values are "
+                        "served from L2/shared memory here, so 'achieved' may exceed the HBM peak -- 'compulsory' is what must cross HBM"}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory; H2D + kernels + D2H inside)
+    e2e = None
+    if args.workload != "c5" and not args.no_e2e:
+        Qe = Q if D == 1 else min(Q, max(1, (1 << 30) // (D * 8)))
+        hq = torch.empty((Qe, N), dtype=torch.float64).pin_memory()
+        hq.copy_(q[:Qe].cpu())
+        ho = torch.empty((Qe, D), dtype=torch.float64).pin_memory()
+        hl = torch.empty(Qe, dtype=torch.int32).pin_memory()
+        hs = torch.empty(Qe, dtype=torch.uint8).pin_memory()
+        n_e2e = max(2, min(args.steps, 3))
+        m.eval_raw(hq.data_ptr(), Qe, ho.data_ptr(), hl.data_ptr(), hs.data_ptr())
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            m.eval_raw(hq.data_ptr(), Qe, ho.data_ptr(), hl.data_ptr(), hs.data_ptr())
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * Qe / dt, "unit": "queries/s", "h2d_bytes_per_step": Qe * N * 8, "d2h_bytes_per_step": Qe * (D * 8 + 5),
+               "queries_per_step_per_gpu": Qe, "ms_per_step": dt * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[args.workload]
+        try:
+            cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, args.workload)
+        except SystemExit as e:
+            cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port", "sample": str(e)}
+
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                          "roofline": roofline, "cpu_baseline": cpu, "wall_s": wall, "bad_status": bad,
+                          "model": {k: info[k] for k in ("n_leaves", "n_samples", "n_terms", "max_support", "depth", "device_bytes")}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

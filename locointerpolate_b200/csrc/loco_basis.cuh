@@ -112,4 +112,21 @@ __device__ __forceinline__ double term_value(const double *__restrict__ cs, doub
 	return value * weight;
 }
 
+// same as term_value with the term's (c, s) pairs in SHARED memory (broadcast reads) and the weight
+// already multiplied by the sample value
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double term_value_smem(const double *cs, double wv, const Coord<NT> &x, int Nrt)
+{
+	const int N = NT > 0 ? NT : Nrt;
+	double value = 1.0;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double2 c = reinterpret_cast<const double2 *>(cs)[d];
+		const double diff = x.get(d) - c.x;
+		const double u = EXACT ? diff * c.y : diff / c.y;
+		value *= CUBIC ? cubic_1d(u) : linear_1d(u);
+	}
+	return value * wv;
+}
+
 } // namespace loco

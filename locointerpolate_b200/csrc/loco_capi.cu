@@ -41,6 +41,9 @@ struct loco_model {
 	DeviceModel dm{};
 	std::vector<void *> allocs;
 	double *d_values = nullptr;
+	double *d_term_wv = nullptr;
+	int64_t n_terms = 0;
+	int sm_count = 148;
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
@@ -100,6 +103,15 @@ std::vector<int32_t> narrow(loco_model *m, const std::vector<T> &v, bool *ok)
 	return r;
 }
 
+// scalar functions: term_wv[t] = weight_t * value(sample of t), used by the leaf-sorted tile path
+int refresh_term_wv(loco_model *m)
+{
+	if (m->dm.D == 1) m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
+	CUDA_OK(m, cudaGetLastError());
+	CUDA_OK(m, cudaDeviceSynchronize());
+	return LOCO_OK;
+}
+
 int build_device_model(loco_model *m)
 {
 	if (m->device == LOCO_HOST_ONLY) {
@@ -148,6 +160,13 @@ int build_device_model(loco_model *m)
 	m->device_bytes += (int64_t)vbytes;
 	CUDA_OK(m, cudaMemset(m->d_values, 0, vbytes));
 	dm.values = m->d_values;
+	m->n_terms = (int64_t)f.term_w.size();
+	CUDA_OK(m, cudaMalloc((void **)&m->d_term_wv, (size_t)(m->n_terms + 2) * sizeof(double)));
+	m->allocs.push_back(m->d_term_wv);
+	m->device_bytes += (int64_t)((m->n_terms + 2) * sizeof(double));
+	CUDA_OK(m, cudaMemset(m->d_term_wv, 0, (size_t)(m->n_terms + 2) * sizeof(double)));
+	dm.term_wv = m->d_term_wv;
+	CUDA_OK(m, cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
 	if (!f.values.empty()) {
 		if ((rc = loco_model_set_values(m, f.values.data()))) return rc;
 	}
@@ -178,7 +197,17 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 	const DeviceModel &dm = m->dm;
 	if (Q <= 0) return LOCO_OK;
 	if (dm.D == 1) {
-		m->launches += in_cube ? launch_eval_scalar_in_cube(dm, q, Q, out, leaf, status, st) : launch_eval_scalar_direct(dm, q, Q, out, leaf, status, st);
+		// leaf-sorted tiles pay off once a leaf bucket fills a good part of a 256-query tile
+		const bool tiles = !in_cube && (m->opt_path == 2 || (m->opt_path == 0 && Q >= (int64_t)dm.L * 48));
+		if (tiles) {
+			int rc;
+			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+			if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
+			m->launches += launch_eval_scalar_tiles(dm, q, Q, out, leaf, status, carve_sort_work(dm, Q, w.misc), m->sm_count, st);
+		} else {
+			m->launches += in_cube ? launch_eval_scalar_in_cube(dm, q, Q, out, leaf, status, st) : launch_eval_scalar_direct(dm, q, Q, out, leaf, status, st);
+		}
 		CUDA_OK(m, cudaGetLastError());
 		return LOCO_OK;
 	}
@@ -372,7 +401,7 @@ int loco_model_set_values(loco_model_t *m, const double *values)
 	const DeviceModel &dm = m->dm;
 	CUDA_OK(m, cudaMemcpy2D(m->d_values, (size_t)dm.value_stride * sizeof(double), values, (size_t)dm.D * sizeof(double),
 	                        (size_t)dm.D * sizeof(double), (size_t)dm.R, cudaMemcpyHostToDevice));
-	return LOCO_OK;
+	return refresh_term_wv(m);
 }
 
 int loco_model_fill_values_synthetic(loco_model_t *m, double seed)
@@ -382,8 +411,7 @@ int loco_model_fill_values_synthetic(loco_model_t *m, double seed)
 	CUDA_OK(m, cudaSetDevice(m->device));
 	m->launches += launch_fill_values(m->d_values, m->dm.R, m->dm.D, m->dm.value_stride, seed, nullptr);
 	CUDA_OK(m, cudaGetLastError());
-	CUDA_OK(m, cudaDeviceSynchronize());
-	return LOCO_OK;
+	return refresh_term_wv(m);
 }
 
 int loco_model_get_values(const loco_model_t *m, int64_t row0, int64_t n, double *out)

@@ -24,6 +24,7 @@ struct DeviceModel {
 	const double *term_w;             // [sum T]
 	const int32_t *term_slot;         // [sum T]
 	const int32_t *term_row;          // [sum T]
+	const double *term_wv;            // [sum T + 2] weight * value of the owning sample (scalar functions only)
 	const double *values;             // [R * value_stride]
 };
 
@@ -56,5 +57,19 @@ int launch_gather_rows(const DeviceModel &m, const int32_t *rows, int64_t n, dou
 int launch_jitter_points(const DeviceModel &m, int64_t points_per_leaf, uint64_t seed, int64_t first, int64_t count,
                          const double *amp, const double *phase, int32_t n_terms, double *q_out, int32_t *leaf_out,
                          double *truth_out, cudaStream_t st);
+
+// ---- leaf-sorted tile path (loco_tiles.cu)
+struct SortWork {
+	int32_t *count;     // [L] queries per leaf
+	int32_t *cursor;    // [L] scatter cursors
+	int32_t *offset;    // [L+1] bucket offsets
+	int32_t *tile_off;  // [L+1] tile offsets
+	int32_t *perm;      // [Q] query indices grouped by leaf
+};
+size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
+SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
+int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
+int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
+                             int sm_count, cudaStream_t st);
 
 } // namespace loco

@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(256) mesh_gather_kernel(DeviceModel m, const d
 	__syncthreads();
 	double *o = out + qi * out_stride;
 	const double nan = __longlong_as_double(0x7ff8000000000000LL);
-	const int D2 = m.D >> 1;
+	// 128-bit path needs 16-byte aligned output rows (value rows always are: value_stride is even for D > 1)
+	const bool vec = ((out_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+	const int D2 = vec ? (m.D >> 1) : 0;
 	for (int j = threadIdx.x; j < D2; j += blockDim.x) {
 		double2 acc = make_double2(0.0, 0.0);
 		if (ok) {
@@ -162,9 +164,8 @@ __global__ void __launch_bounds__(256) mesh_gather_kernel(DeviceModel m, const d
 		}
 		reinterpret_cast<double2 *>(o)[j] = acc;
 	}
-	if ((m.D & 1) && threadIdx.x == 0) {
+	for (int j = 2 * D2 + threadIdx.x; j < m.D; j += blockDim.x) {
 		double acc = 0.0;
-		const int j = m.D - 1;
 		if (ok) for (int k = 0; k < K; k++) acc += sw[k] * m.values[(int64_t)srow[k] * m.value_stride + j];
 		else acc = nan;
 		o[j] = acc;

@@ -1,0 +1,297 @@
+// loco_tiles.cu -- leaf-sorted tile path (the throughput path for scalar functions).
+//
+// The direct path (loco_kernels.cu) lets every thread walk its own leaf's term list: with 10^4..10^5 leaves
+// the lists of one warp are 32 different 4 KB blocks and the kernel is bound by L2 gather latency.
+// Here the batch is counting-sorted by containing leaf first, so that a CTA works on up to TILE_Q
+// queries of ONE leaf: the leaf's terms are staged once into shared memory by the TMA engine
+// (cp.async.bulk + mbarrier) and every thread then evaluates its own query against broadcast shared-memory
+// reads -- no divergence, no per-thread gathers.  Results are scattered back to the caller's order, so the
+// output does not depend on the (non-deterministic) order inside a leaf bucket.
+//
+//   1. locate_count   map -> descend -> containment; leaf[], status[]; histogram of leaves (REDG atomics)
+//   2. scan           exclusive scan of the histogram -> bucket offsets and tile offsets (one CTA)
+//   3. scatter        perm[offset[leaf] + cursor[leaf]++] = query index
+//   4. eval_tiles     persistent CTAs over contiguous tile ranges; terms via TMA bulk copies
+//
+// Reference semantics: identical to the direct path (see loco_kernels.cu); for D == 1 the per-term
+// weight and the sample value are pre-multiplied (term_wv = weight_ * val), which only re-associates
+// LCRealFunctionValue::add's  val += w * other  (w = sum of the sample's terms).
+#include <algorithm>
+
+#include "loco_basis.cuh"
+#include "loco_device.h"
+
+namespace loco {
+
+// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	const uint32_t addr = smem_u32(bar);
+	while (!done) {
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+	}
+}
+// global -> shared bulk copy executed by the TMA engine; size and both addresses are multiples of 16 B
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 1. locate + histogram
+// ---------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256) locate_count_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
+                                                            uint8_t *__restrict__ status_out, int32_t *__restrict__ count, double *__restrict__ out)
+{
+	const int N = NT > 0 ? NT : m.N;
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= Q) return;
+	Coord<NT> x;
+	map_to_cube<NT>(m, q + i * N, x);
+	const int32_t leaf = descend<NT>(m, x);
+	uint8_t st = containment_status<NT>(m, x, leaf);
+	if (st == ST_OK) st = m.leaf_status[leaf];
+	leaf_out[i] = leaf;
+	status_out[i] = st;
+	if (st == ST_OK) atomicAdd(count + leaf, 1);
+	else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2. exclusive scan over leaves (single CTA): bucket offsets and tile offsets
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_leaves_kernel(const int32_t *__restrict__ count, int32_t L, int32_t tile_q, int32_t *__restrict__ offset,
+                                                            int32_t *__restrict__ tile_off)
+{
+	__shared__ int2 warp_sums[32];
+	__shared__ int2 carry;
+	if (threadIdx.x == 0) carry = make_int2(0, 0);
+	__syncthreads();
+	for (int32_t base = 0; base < L; base += 1024) {
+		const int32_t l = base + threadIdx.x;
+		const int c = l < L ? count[l] : 0;
+		int2 v = make_int2(c, (c + tile_q - 1) / tile_q);
+		int2 incl = v;
+		for (int off = 1; off < 32; off <<= 1) {
+			int a = __shfl_up_sync(0xffffffffu, incl.x, off), b = __shfl_up_sync(0xffffffffu, incl.y, off);
+			if ((threadIdx.x & 31) >= off) { incl.x += a; incl.y += b; }
+		}
+		if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			int2 w = warp_sums[threadIdx.x], wi = w;
+			for (int off = 1; off < 32; off <<= 1) {
+				int a = __shfl_up_sync(0xffffffffu, wi.x, off), b = __shfl_up_sync(0xffffffffu, wi.y, off);
+				if (threadIdx.x >= off) { wi.x += a; wi.y += b; }
+			}
+			warp_sums[threadIdx.x] = make_int2(wi.x - w.x, wi.y - w.y);  // exclusive prefix of the warp totals
+		}
+		__syncthreads();
+		const int2 wbase = warp_sums[threadIdx.x >> 5], cr = carry;
+		if (l < L) {
+			offset[l] = cr.x + wbase.x + incl.x - v.x;
+			tile_off[l] = cr.y + wbase.y + incl.y - v.y;
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = make_int2(cr.x + wbase.x + incl.x, cr.y + wbase.y + incl.y);
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { offset[L] = carry.x; tile_off[L] = carry.y; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. scatter query indices into their leaf buckets
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_kernel(const int32_t *__restrict__ leaf, const uint8_t *__restrict__ status, int64_t Q,
+                                                       const int32_t *__restrict__ offset, int32_t *__restrict__ cursor, int32_t *__restrict__ perm)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= Q || status[i] != ST_OK) return;
+	const int32_t l = leaf[i];
+	perm[offset[l] + atomicAdd(cursor + l, 1)] = (int32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4. evaluation over leaf tiles
+// ---------------------------------------------------------------------------------------------------
+template <int NT, bool CUBIC, bool EXACT, int TILE_Q>
+__global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const double *__restrict__ q, double *__restrict__ out,
+                                                             const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off,
+                                                             const int32_t *__restrict__ perm, int32_t chunk_terms)
+{
+	const int N = NT > 0 ? NT : m.N;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *s_cs = reinterpret_cast<double *>(smem_raw);  // [chunk_terms * 2N]
+	double *s_wv = s_cs + (size_t)chunk_terms * 2 * N;     // [chunk_terms + 2]
+	__shared__ __align__(8) uint64_t bar;
+	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	uint32_t phase = 0;
+
+	const int32_t L = m.L;
+	const int64_t total = tile_off[L];
+	const int64_t t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
+	int32_t leaf = -1, leaf_tile0 = 0, leaf_tile1 = 0;  // tiles [leaf_tile0, leaf_tile1) belong to `leaf`
+	int32_t staged_leaf = -1;                            // leaf whose (single-chunk) term list sits in shared memory
+
+	for (int64_t tile = t_begin; tile < t_end; tile++) {
+		if (tile >= leaf_tile1) {
+			// last leaf whose first tile is <= tile (empty leaves have no tiles and are skipped by the upper bound)
+			int32_t lo = leaf < 0 ? 0 : leaf + 1, hi = L;
+			while (lo < hi) {
+				const int32_t mid = (lo + hi) >> 1;
+				if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
+			}
+			leaf = lo;
+			leaf_tile0 = __ldg(tile_off + leaf);
+			leaf_tile1 = __ldg(tile_off + leaf + 1);
+		}
+		const int32_t qbeg = __ldg(offset + leaf) + (int32_t)(tile - leaf_tile0) * TILE_Q;
+		const int32_t qend = min(qbeg + TILE_Q, __ldg(offset + leaf + 1));
+		const int32_t pos = qbeg + threadIdx.x;
+		const bool active = pos < qend;
+		int32_t qi = 0;
+		Coord<NT> x;
+		if (active) {
+			qi = __ldg(perm + pos);
+			map_to_cube<NT>(m, q + (int64_t)qi * N, x);
+		} else {
+#pragma unroll
+			for (int d = 0; d < (NT > 0 ? NT : 1); d++) x.set(d, 0.0);
+			if (NT == 0) for (int d = 0; d < N; d++) x.set(d, 0.0);
+		}
+		const int32_t T0 = __ldg(m.term_off + leaf), T1 = __ldg(m.term_off + leaf + 1);
+		double acc = 0.0;
+		for (int32_t c0 = T0; c0 < T1; c0 += chunk_terms) {
+			const int32_t c1 = min(c0 + chunk_terms, T1);
+			const int32_t a0 = c0 & ~1;  // term_wv is copied from an even index so that the source is 16-byte aligned
+			if (!(staged_leaf == leaf && T1 - T0 <= chunk_terms)) {
+				__syncthreads();  // everyone is done with the previous contents
+				if (threadIdx.x == 0) {
+					const uint32_t cs_bytes = (uint32_t)(c1 - c0) * 2 * N * 8;
+					const uint32_t wv_bytes = (uint32_t)(((c1 + 1) & ~1) - a0) * 8;
+					mbar_expect_tx(&bar, cs_bytes + wv_bytes);
+					tma_bulk_g2s(s_cs, m.term_cs + (int64_t)c0 * 2 * N, cs_bytes, &bar);
+					tma_bulk_g2s(s_wv, m.term_wv + a0, wv_bytes, &bar);
+				}
+				mbar_wait(&bar, phase);
+				phase ^= 1;
+				staged_leaf = (T1 - T0 <= chunk_terms) ? leaf : -1;
+			}
+			const double *wv = s_wv + (c0 - a0);
+			const int n = c1 - c0;
+#pragma unroll 2
+			for (int t = 0; t < n; t++) acc += term_value_smem<NT, CUBIC, EXACT>(s_cs + (size_t)t * 2 * N, wv[t], x, N);
+		}
+		if (active) out[qi] = acc;
+	}
+}
+
+// term_wv[t] = term_w[t] * values[term_row[t]]   (scalar functions; refreshed whenever the value table changes)
+__global__ void term_wv_kernel(DeviceModel m, double *__restrict__ term_wv, int64_t T)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < T) term_wv[t] = m.term_w[t] * m.values[(int64_t)m.term_row[t] * m.value_stride];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+namespace {
+const int kTileQ = 256;
+
+template <int NT>
+void locate_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, int32_t *count, double *out, cudaStream_t st)
+{
+	locate_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, count, out);
+}
+
+template <int NT, bool CUBIC, bool EXACT>
+void eval_tiles(const DeviceModel &m, const double *q, double *out, const SortWork &w, int chunk_terms, size_t smem, int grid, cudaStream_t st)
+{
+	auto kern = eval_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
+	kern<<<grid, kTileQ, smem, st>>>(m, q, out, w.offset, w.tile_off, w.perm, chunk_terms);
+}
+} // namespace
+
+size_t sort_work_bytes(const DeviceModel &m, int64_t Q)
+{
+	return ((size_t)m.L * 2 + (size_t)(m.L + 1) * 2 + (size_t)Q) * sizeof(int32_t) + 256;
+}
+
+SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base)
+{
+	SortWork w;
+	int32_t *p = reinterpret_cast<int32_t *>(base);
+	w.count = p; p += m.L;
+	w.cursor = p; p += m.L;
+	w.offset = p; p += m.L + 1;
+	w.tile_off = p; p += m.L + 1;
+	w.perm = p;
+	(void)Q;
+	return w;
+}
+
+int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st)
+{
+	if (T <= 0) return 0;
+	term_wv_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(m, term_wv, T);
+	return 1;
+}
+
+int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
+                             int sm_count, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	cudaMemsetAsync(w.count, 0, (size_t)m.L * 2 * sizeof(int32_t), st);  // count and cursor are adjacent
+	switch (m.N <= kMaxTemplateN ? m.N : 0) {
+	case 1: locate_count<1>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 2: locate_count<2>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 3: locate_count<3>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 4: locate_count<4>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 5: locate_count<5>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 6: locate_count<6>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 7: locate_count<7>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 8: locate_count<8>(m, q, Q, leaf, status, w.count, out, st); break;
+	default: locate_count<0>(m, q, Q, leaf, status, w.count, out, st); break;
+	}
+	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, kTileQ, w.offset, w.tile_off);
+	scatter_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(leaf, status, Q, w.offset, w.cursor, w.perm);
+
+	const int per_term = 2 * m.N * 8 + 8;
+	int chunk = (40 * 1024) / per_term;
+	chunk = std::max(2, std::min(chunk & ~1, (m.max_terms + 1) & ~1));
+	const size_t smem = (size_t)chunk * 2 * m.N * 8 + (size_t)(chunk + 2) * 8;
+	const int64_t max_tiles = Q / kTileQ + m.L + 1;
+	const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)sm_count * 8);
+	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
+#define LOCO_TCASE(NT)                                                                                                   \
+	case NT:                                                                                                             \
+		if (cubic) { if (exact) eval_tiles<NT, true, true>(m, q, out, w, chunk, smem, grid, st); else eval_tiles<NT, true, false>(m, q, out, w, chunk, smem, grid, st); } \
+		else { if (exact) eval_tiles<NT, false, true>(m, q, out, w, chunk, smem, grid, st); else eval_tiles<NT, false, false>(m, q, out, w, chunk, smem, grid, st); }     \
+		break;
+	switch (m.N <= kMaxTemplateN ? m.N : 0) {
+		LOCO_TCASE(0) LOCO_TCASE(1) LOCO_TCASE(2) LOCO_TCASE(3) LOCO_TCASE(4) LOCO_TCASE(5) LOCO_TCASE(6) LOCO_TCASE(7) LOCO_TCASE(8)
+	}
+#undef LOCO_TCASE
+	return 4;
+}
+
+} // namespace loco
