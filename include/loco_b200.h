@@ -192,7 +192,7 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
                                       uint8_t *split, void *cuda_stream);
 
 /* ---- tuning / accounting -------------------------------------------------------------------------------- */
-/* options: "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted tiles;  "fp32" 0|1 (scalar weights in fp32) */
+/* options: "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted tiles | 3 direct without the tensor-leaf shortcut;  "fp32" 0|1 (scalar weights in fp32) */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);

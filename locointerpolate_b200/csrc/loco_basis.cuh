@@ -71,6 +71,104 @@ __device__ __forceinline__ uint8_t containment_status(const DeviceModel &m, cons
 	return outside ? (uint8_t)ST_OUTSIDE_CELL : (uint8_t)ST_OK;
 }
 
+// The same test for a leaf REACHED BY DESCENT in a tree whose leaf boxes are exactly the boxes implied by
+// the split planes (DeviceModel::path_consistent, verified at flatten time): the descent already guarantees
+// lo_d <= x_d (child2: not x < split) and x_d < hi_d (child1) on every split plane, so the +-EPSILON test
+// can only fail on a face of the ROOT box, where leaf bound == root bound bit for bit.  No per-leaf loads.
+template <int NT>
+__device__ __forceinline__ uint8_t located_status(const DeviceModel &m, const Coord<NT> &x, int32_t leaf)
+{
+	if (!m.path_consistent) {
+		uint8_t st = containment_status<NT>(m, x, leaf);
+		if (st == ST_OK) st = m.leaf_status[leaf];
+		return st;
+	}
+	const int N = NT > 0 ? NT : m.N;
+	bool outside = false;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double xv = x.get(d);
+		outside |= (xv < m.root_lo_eps[d]) || (xv > m.root_hi_eps[d]);
+	}
+	uint8_t st = outside ? (uint8_t)ST_OUTSIDE_CELL : (uint8_t)ST_OK;
+	if (st == ST_OK && m.any_leaf_status) st = m.leaf_status[leaf];
+	return st;
+}
+
+__device__ __forceinline__ double linear_1d(double u);
+__device__ __forceinline__ double cubic_1d(double u);
+
+// ---- tensor-product leaves -------------------------------------------------------------------------------
+// f[d][j] = b((x_d - c_d[j]) / s_d): the N*F one-dimensional factors of a leaf block (see DeviceModel)
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ void tensor_factors(const double *blk, const Coord<NT> &x, double (&f)[NT][CUBIC ? 4 : 2])
+{
+	constexpr int F = CUBIC ? 4 : 2;
+#pragma unroll
+	for (int d = 0; d < NT; d++) {
+		const double r = blk[NT * F + d];
+		const double xv = x.get(d);
+#pragma unroll
+		for (int j = 0; j < F; j++) {
+			const double diff = xv - blk[d * F + j];
+			const double u = EXACT ? diff * r : diff / r;
+			f[d][j] = CUBIC ? cubic_1d(u) : linear_1d(u);
+		}
+	}
+}
+
+// sum over the F^(LEVEL+1) leading entries of v (dimension 0 fastest) of prod_{d<=LEVEL} f[d][j_d] * v[...]
+// -- LCFunctionValue::newFromWeightedSum with w_k = prod_d f[d][j_d], evaluated by sum factorisation.
+template <int F>
+__device__ __forceinline__ double pick_factor(const double (&row)[F], int j)
+{
+	double r = row[0];
+#pragma unroll
+	for (int i = 1; i < F; i++) r = (i == j) ? row[i] : r;
+	return r;
+}
+__host__ __device__ constexpr int ipow_c(int b, int e) { return e <= 0 ? 1 : b * ipow_c(b, e - 1); }
+
+template <int NT, int F, int LEVEL>
+struct TensorContract {
+	static __device__ __forceinline__ double run(const double *v, const double (&f)[NT][F], int stride)
+	{
+		double s = 0.0;
+		if (ipow_c(F, LEVEL + 1) > 64) {
+			// outer levels of big tensors stay rolled (code size); the factor is picked by a select chain so
+			// that f[][] is never indexed dynamically and stays in registers
+#pragma unroll 1
+			for (int j = 0; j < F; j++) s += pick_factor<F>(f[LEVEL], j) * TensorContract<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, f, stride / F);
+		} else {
+#pragma unroll
+			for (int j = 0; j < F; j++) s += f[LEVEL][j] * TensorContract<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, f, stride / F);
+		}
+		return s;
+	}
+};
+template <int NT, int F>
+struct TensorContract<NT, F, 0> {
+	static __device__ __forceinline__ double run(const double *v, const double (&f)[NT][F], int)
+	{
+		double s = 0.0;
+#pragma unroll
+		for (int j = 0; j < F; j += 2) {
+			const double2 p = *reinterpret_cast<const double2 *>(v + j);
+			s += f[0][j] * p.x;
+			s += f[0][j + 1] * p.y;
+		}
+		return s;
+	}
+};
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double tensor_eval_scalar(const DeviceModel &m, const double *blk, const Coord<NT> &x)
+{
+	constexpr int F = CUBIC ? 4 : 2;
+	double f[NT][F];
+	tensor_factors<NT, CUBIC, EXACT>(blk, x, f);
+	return TensorContract<NT, F, NT - 1>::run(blk + m.tl_voff, f, m.tensor_K / F);
+}
+
 // One dimension of LCLinearBSpline::eval (LCBasisFunction.cpp:283-288): d = |x-c|/s; d <= 1 ? 1-d : 0.
 // u = (x-c)/s is passed in.
 __device__ __forceinline__ double linear_1d(double u)

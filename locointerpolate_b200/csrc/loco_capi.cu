@@ -42,6 +42,7 @@ struct loco_model {
 	std::vector<void *> allocs;
 	double *d_values = nullptr;
 	double *d_term_wv = nullptr;
+	double *d_tl_block = nullptr;
 	int64_t n_terms = 0;
 	int sm_count = 148;
 	int64_t device_bytes = 0;
@@ -106,7 +107,10 @@ std::vector<int32_t> narrow(loco_model *m, const std::vector<T> &v, bool *ok)
 // scalar functions: term_wv[t] = weight_t * value(sample of t), used by the leaf-sorted tile path
 int refresh_term_wv(loco_model *m)
 {
-	if (m->dm.D == 1) m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
+	if (m->dm.D == 1) {
+		m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
+		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, nullptr);
+	}
 	CUDA_OK(m, cudaGetLastError());
 	CUDA_OK(m, cudaDeviceSynchronize());
 	return LOCO_OK;
@@ -167,6 +171,31 @@ int build_device_model(loco_model *m)
 	CUDA_OK(m, cudaMemset(m->d_term_wv, 0, (size_t)(m->n_terms + 2) * sizeof(double)));
 	dm.term_wv = m->d_term_wv;
 	CUDA_OK(m, cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
+	// tensor-product leaf blocks
+	dm.tensor_F = 0;
+	if (f.tensor_F > 0 && f.N <= kMaxTemplateN) {
+		const int F = f.tensor_F, K = f.tensor_K, N = f.N;
+		dm.tensor_F = F; dm.tensor_K = K;
+		dm.tl_voff = (N * F + N + 1) & ~1;
+		dm.tl_stride = f.D == 1 ? ((dm.tl_voff + K + 1) & ~1) : dm.tl_voff;
+		std::vector<double> blk((size_t)f.L * dm.tl_stride, 0.0);
+		for (int64_t l = 0; l < f.L; l++) {
+			double *b = &blk[(size_t)l * dm.tl_stride];
+			std::copy(f.tl_center.begin() + l * N * F, f.tl_center.begin() + (l + 1) * N * F, b);
+			std::copy(f.tl_rcp.begin() + l * N, f.tl_rcp.begin() + (l + 1) * N, b + N * F);
+		}
+		const double *dblk = nullptr;
+		if ((rc = upload(m, blk, &dblk))) return rc;
+		m->d_tl_block = const_cast<double *>(dblk);
+		dm.tl_block = dblk;
+		if ((rc = upload(m, f.tl_row, &dm.tl_row))) return rc;
+	}
+	dm.path_consistent = f.path_consistent ? 1 : 0;
+	dm.any_leaf_status = f.any_leaf_status ? 1 : 0;
+	for (int i = 0; i < f.N; i++) {
+		dm.root_lo_eps[i] = m->graph.tree.ranges[2 * i] - kEpsilon;
+		dm.root_hi_eps[i] = m->graph.tree.ranges[2 * i + 1] + kEpsilon;
+	}
 	if (!f.values.empty()) {
 		if ((rc = loco_model_set_values(m, f.values.data()))) return rc;
 	}
@@ -198,13 +227,17 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 	if (Q <= 0) return LOCO_OK;
 	if (dm.D == 1) {
 		// leaf-sorted tiles pay off once a leaf bucket fills a good part of a 256-query tile
-		const bool tiles = !in_cube && (m->opt_path == 2 || (m->opt_path == 0 && Q >= (int64_t)dm.L * 48));
+		// and the per-leaf data no longer sits in the L1 anyway
+		const int64_t leaf_bytes = dm.tensor_F > 0 ? (int64_t)dm.L * dm.tl_stride * 8 : m->n_terms * (16 * dm.N + 8);
+		const bool tiles = !in_cube && (m->opt_path == 2 || (m->opt_path == 0 && Q >= (int64_t)dm.L * 48 && leaf_bytes > 96 * 1024));
 		if (tiles) {
 			int rc;
 			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
 			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
 			if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
 			m->launches += launch_eval_scalar_tiles(dm, q, Q, out, leaf, status, carve_sort_work(dm, Q, w.misc), m->sm_count, st);
+		} else if (dm.tensor_F > 0 && m->opt_path != 3) {
+			m->launches += launch_eval_scalar_tensor_direct(dm, in_cube, q, Q, out, leaf, status, st);
 		} else {
 			m->launches += in_cube ? launch_eval_scalar_in_cube(dm, q, Q, out, leaf, status, st) : launch_eval_scalar_direct(dm, q, Q, out, leaf, status, st);
 		}

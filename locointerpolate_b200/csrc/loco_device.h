@@ -6,6 +6,9 @@
 
 namespace loco {
 
+const int kMaxTemplateN = 8;   // N = 1..8 get fully unrolled kernels
+const int kMaxN = 16;          // larger N use the runtime-N instantiation (coordinates in local memory)
+
 // Pointers into HBM; passed by value to every kernel.  Layout documented in DESIGN.md ("HBM layout").
 struct DeviceModel {
 	int32_t N, D, basis, exact_rcp;
@@ -26,10 +29,16 @@ struct DeviceModel {
 	const int32_t *term_row;          // [sum T]
 	const double *term_wv;            // [sum T + 2] weight * value of the owning sample (scalar functions only)
 	const double *values;             // [R * value_stride]
+	// tensor-product leaves (tensor_F > 0): one block of tl_stride doubles per leaf,
+	//   [N*F centres | N supports-or-reciprocals | pad to even | F^N sample values in tensor order (D == 1 only)]
+	int32_t tensor_F, tensor_K, tl_stride, tl_voff;
+	const double *tl_block;           // [L * tl_stride]
+	const int32_t *tl_row;            // [L * F^N] value rows in tensor order
+	// containment against the root box only (valid when every leaf box is implied by its split planes)
+	int32_t path_consistent, any_leaf_status;
+	double root_lo_eps[kMaxN], root_hi_eps[kMaxN];
 };
 
-const int kMaxTemplateN = 8;   // N = 1..8 get fully unrolled kernels
-const int kMaxN = 16;          // larger N use the runtime-N instantiation (coordinates in local memory)
 
 // ---- launchers (loco_kernels.cu).  All asynchronous on `st`; return the number of kernels launched.
 // fused map -> locate -> weights -> weighted sum for scalar functions (D == 1), one thread per query
@@ -69,6 +78,9 @@ struct SortWork {
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
+int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, cudaStream_t st);
+int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
+                                     cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
 

@@ -65,6 +65,24 @@ struct Flat {
 	std::vector<int32_t> sample_row;   // [S]
 	std::vector<double> values;        // [R*D] (may be empty when the table is filled on the device)
 
+	// ---- tensor-product leaves ---------------------------------------------------------------------
+	// On bootstrap-uniform grids every leaf's term list is a full tensor product: one unit-weight basis
+	// function per influencing sample, F distinct centres per dimension (F = 2 linear / 4 cubic), one
+	// common support per dimension, all F^N combinations present.  Then w_k = prod_d b((x_d - c_d[j_d]) / s_d)
+	// needs only N*F one-dimensional evaluations instead of N*F^N.  tensor_F > 0 iff EVERY leaf has this
+	// structure with the same F; the generic term lists above stay valid either way.
+	int32_t tensor_F = 0;
+	int32_t tensor_K = 0;                 // F^N
+	std::vector<double> tl_center;        // [L * N * F] ascending per dimension
+	std::vector<double> tl_rcp;           // [L * N]     support (or 1/support when exact_rcp)
+	std::vector<int32_t> tl_slot;         // [L * F^N]   slot in the leaf's sorted support list, tensor order (dimension 0 fastest)
+	std::vector<int32_t> tl_row;          // [L * F^N]   value row, same order
+
+	// every leaf box equals the box implied by the split planes on its root path: the +-EPSILON containment
+	// test can then only fail at the root box, and no per-leaf bounds need to be read per query
+	bool path_consistent = false;
+	bool any_leaf_status = false;
+
 	// leaf adjacency kept for introspection / tests
 	std::vector<int32_t> n_leaf_neighbors, n_border_neighbors;  // [L]
 };

@@ -247,6 +247,88 @@ Status flatten(const Graph &g, Flat *out)
 		f.max_terms = std::max<int32_t>(f.max_terms, (int32_t)(f.term_off[(size_t)l + 1] - f.term_off[(size_t)l]));
 	}
 
+	// ---- tensor-product structure (see loco_flat.h) ---------------------------------------------------
+	{
+		const int F = cubic ? 4 : 2;
+		int64_t KT = 1;
+		for (int i = 0; i < N && KT <= (1 << 20); i++) KT *= F;
+		bool all = L > 0 && KT <= (1 << 16);
+		std::vector<double> cen((size_t)N * F);
+		std::vector<int32_t> hit;
+		for (int64_t l = 0; l < L && all; l++) {
+			const int64_t t0 = f.term_off[(size_t)l], t1 = f.term_off[(size_t)l + 1];
+			if (t1 - t0 != KT || f.sup_off[(size_t)l + 1] - f.sup_off[(size_t)l] != KT) { all = false; break; }
+			// distinct centres per dimension, common support per dimension, unit weights
+			std::vector<int> nc((size_t)N, 0);
+			for (int64_t t = t0; t < t1 && all; t++) {
+				if (f.term_w[(size_t)t] != 1.0) all = false;
+				for (int i = 0; i < N && all; i++) {
+					const double c = f.term_cs[(size_t)t * 2 * N + 2 * i], r = f.term_cs[(size_t)t * 2 * N + 2 * i + 1];
+					if (r != f.term_cs[(size_t)t0 * 2 * N + 2 * i + 1]) { all = false; break; }
+					bool found = false;
+					for (int j = 0; j < nc[(size_t)i]; j++) found |= cen[(size_t)i * F + j] == c;
+					if (!found) {
+						if (nc[(size_t)i] == F) { all = false; break; }
+						cen[(size_t)i * F + nc[(size_t)i]++] = c;
+					}
+				}
+			}
+			for (int i = 0; i < N && all; i++) {
+				if (nc[(size_t)i] != F) all = false;
+				std::sort(cen.begin() + (size_t)i * F, cen.begin() + (size_t)(i + 1) * F);
+			}
+			if (!all) break;
+			hit.assign((size_t)KT, -1);
+			for (int64_t t = t0; t < t1 && all; t++) {
+				int64_t idx = 0, mul = 1;
+				for (int i = 0; i < N; i++) {
+					const double c = f.term_cs[(size_t)t * 2 * N + 2 * i];
+					int j = 0;
+					while (cen[(size_t)i * F + j] != c) j++;
+					idx += j * mul;
+					mul *= F;
+				}
+				if (hit[(size_t)idx] >= 0) all = false;
+				hit[(size_t)idx] = (int32_t)(t - t0);
+			}
+			if (!all) break;
+			f.tl_center.insert(f.tl_center.end(), cen.begin(), cen.end());
+			for (int i = 0; i < N; i++) f.tl_rcp.push_back(f.term_cs[(size_t)t0 * 2 * N + 2 * i + 1]);
+			for (int64_t j = 0; j < KT; j++) {
+				f.tl_slot.push_back(f.term_slot[(size_t)(t0 + hit[(size_t)j])]);
+				f.tl_row.push_back(f.term_row[(size_t)(t0 + hit[(size_t)j])]);
+			}
+		}
+		if (all) { f.tensor_F = F; f.tensor_K = (int32_t)KT; }
+		else { f.tl_center.clear(); f.tl_rcp.clear(); f.tl_slot.clear(); f.tl_row.clear(); }
+	}
+
+	// ---- are the leaf boxes exactly the boxes implied by the split planes? -----------------------------------
+	{
+		bool ok = true;
+		std::vector<double> lo((size_t)f.C * N), hi((size_t)f.C * N);
+		for (int i = 0; i < N; i++) { lo[i] = g.tree.ranges[2 * i]; hi[i] = g.tree.ranges[2 * i + 1]; }
+		for (int64_t c = 0; c < f.C && ok; c++) {
+			const int32_t dir = g.tree.split_dir[c];
+			if (dir < 0) {
+				const double *r = cx.box(g.tree, c);
+				for (int i = 0; i < N; i++) ok &= (r[2 * i] == lo[(size_t)c * N + i]) && (r[2 * i + 1] == hi[(size_t)c * N + i]);
+				continue;
+			}
+			const int64_t c1 = c + 1, c2 = g.tree.child2[c];
+			const double sv = g.tree.split_val[c];
+			if (!(sv >= lo[(size_t)c * N + dir] && sv <= hi[(size_t)c * N + dir])) ok = false;
+			for (int i = 0; i < N; i++) {
+				lo[(size_t)c1 * N + i] = lo[(size_t)c2 * N + i] = lo[(size_t)c * N + i];
+				hi[(size_t)c1 * N + i] = hi[(size_t)c2 * N + i] = hi[(size_t)c * N + i];
+			}
+			hi[(size_t)c1 * N + dir] = sv;
+			lo[(size_t)c2 * N + dir] = sv;
+		}
+		f.path_consistent = ok;
+	}
+	for (uint8_t s : f.leaf_status) f.any_leaf_status |= s != ST_OK;
+
 	f.sample_row = g.sample_row;
 	f.values = g.values;
 	return Status();

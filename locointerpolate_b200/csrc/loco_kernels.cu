@@ -31,8 +31,9 @@ __global__ void __launch_bounds__(256) eval_scalar_direct_kernel(DeviceModel m, 
 		map_to_cube<NT>(m, q + i * N, x);
 		leaf = descend<NT>(m, x);
 	}
-	uint8_t st = containment_status<NT>(m, x, leaf);
-	if (st == ST_OK) st = m.leaf_status[leaf];
+	uint8_t st;
+	if (IN_CUBE) { st = containment_status<NT>(m, x, leaf); if (st == ST_OK) st = m.leaf_status[leaf]; }
+	else st = located_status<NT>(m, x, leaf);
 	double r = 0.0;  // LCRealFunctionValue(0), LCFunctionValue.cpp:22
 	if (st == ST_OK) {
 		int t = m.term_off[leaf];
@@ -72,8 +73,7 @@ __global__ void __launch_bounds__(256) locate_kernel(DeviceModel m, const double
 	Coord<NT> x;
 	map_to_cube<NT>(m, q + i * N, x);
 	int32_t leaf = descend<NT>(m, x);
-	uint8_t st = containment_status<NT>(m, x, leaf);
-	if (st == ST_OK) st = m.leaf_status[leaf];
+	uint8_t st = located_status<NT>(m, x, leaf);
 	if (xs) for (int d = 0; d < N; d++) xs[i * N + d] = x.get(d);
 	if (leaf_out) leaf_out[i] = leaf;
 	if (status_out) status_out[i] = st;
@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(256) weights_kernel(DeviceModel m, const doubl
 		map_to_cube<NT>(m, q + i * N, x);
 		leaf = descend<NT>(m, x);
 	}
-	uint8_t st = containment_status<NT>(m, x, leaf);
-	if (st == ST_OK) st = m.leaf_status[leaf];
+	uint8_t st;
+	if (IN_CUBE) { st = containment_status<NT>(m, x, leaf); if (st == ST_OK) st = m.leaf_status[leaf]; }
+	else st = located_status<NT>(m, x, leaf);
 	double *w = W + i * (int64_t)m.max_support;
 	const int K = m.sup_off[leaf + 1] - m.sup_off[leaf];
 	for (int k = 0; k < m.max_support; k++) w[k] = 0.0;

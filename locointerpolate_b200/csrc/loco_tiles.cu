@@ -20,38 +20,9 @@
 
 #include "loco_basis.cuh"
 #include "loco_device.h"
+#include "loco_tma.cuh"
 
 namespace loco {
-
-// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-	uint32_t done = 0;
-	const uint32_t addr = smem_u32(bar);
-	while (!done) {
-		asm volatile(
-		    "{\n\t.reg .pred p;\n\t"
-		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-		    "selp.u32 %0, 1, 0, p;\n\t}"
-		    : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-	}
-}
-// global -> shared bulk copy executed by the TMA engine; size and both addresses are multiples of 16 B
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------------
 // 1. locate + histogram
@@ -66,8 +37,7 @@ __global__ void __launch_bounds__(256) locate_count_kernel(DeviceModel m, const 
 	Coord<NT> x;
 	map_to_cube<NT>(m, q + i * N, x);
 	const int32_t leaf = descend<NT>(m, x);
-	uint8_t st = containment_status<NT>(m, x, leaf);
-	if (st == ST_OK) st = m.leaf_status[leaf];
+	const uint8_t st = located_status<NT>(m, x, leaf);
 	leaf_out[i] = leaf;
 	status_out[i] = st;
 	if (st == ST_OK) atomicAdd(count + leaf, 1);
@@ -204,6 +174,63 @@ __global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const
 	}
 }
 
+// Tensor-product leaves: the leaf's block (centres, supports, F^N sample values in tensor order) is one
+// contiguous run of tl_stride doubles -> ONE TMA bulk copy per leaf; each thread then needs N*F
+// one-dimensional basis evaluations and a sum-factorised contraction over shared memory.
+template <int NT, bool CUBIC, bool EXACT, int TILE_Q>
+__global__ void __launch_bounds__(TILE_Q) eval_tensor_tiles_kernel(DeviceModel m, const double *__restrict__ q, double *__restrict__ out,
+                                                                    const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off,
+                                                                    const int32_t *__restrict__ perm)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *s_blk = reinterpret_cast<double *>(smem_raw);  // [tl_stride]
+	__shared__ __align__(8) uint64_t bar;
+	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	uint32_t phase = 0;
+	const int32_t L = m.L;
+	const int64_t total = tile_off[L];
+	const int64_t t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
+	int32_t leaf = -1, leaf_tile0 = 0, leaf_tile1 = 0, staged_leaf = -1;
+	for (int64_t tile = t_begin; tile < t_end; tile++) {
+		if (tile >= leaf_tile1) {
+			int32_t lo = leaf < 0 ? 0 : leaf + 1, hi = L;
+			while (lo < hi) {
+				const int32_t mid = (lo + hi) >> 1;
+				if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
+			}
+			leaf = lo;
+			leaf_tile0 = __ldg(tile_off + leaf);
+			leaf_tile1 = __ldg(tile_off + leaf + 1);
+		}
+		const int32_t qbeg = __ldg(offset + leaf) + (int32_t)(tile - leaf_tile0) * TILE_Q;
+		const int32_t qend = min(qbeg + TILE_Q, __ldg(offset + leaf + 1));
+		const int32_t pos = qbeg + threadIdx.x;
+		const bool active = pos < qend;
+		int32_t qi = 0;
+		Coord<NT> x;
+#pragma unroll
+		for (int d = 0; d < NT; d++) x.set(d, 0.0);
+		if (active) {
+			qi = __ldg(perm + pos);
+			map_to_cube<NT>(m, q + (int64_t)qi * NT, x);
+		}
+		if (staged_leaf != leaf) {
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				const uint32_t bytes = (uint32_t)m.tl_stride * 8;
+				mbar_expect_tx(&bar, bytes);
+				tma_bulk_g2s(s_blk, m.tl_block + (int64_t)leaf * m.tl_stride, bytes, &bar);
+			}
+			mbar_wait(&bar, phase);
+			phase ^= 1;
+			staged_leaf = leaf;
+		}
+		const double r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, s_blk, x);
+		if (active) out[qi] = r;
+	}
+}
+
 // term_wv[t] = term_w[t] * values[term_row[t]]   (scalar functions; refreshed whenever the value table changes)
 __global__ void term_wv_kernel(DeviceModel m, double *__restrict__ term_wv, int64_t T)
 {
@@ -221,6 +248,15 @@ template <int NT>
 void locate_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, int32_t *count, double *out, cudaStream_t st)
 {
 	locate_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, count, out);
+}
+
+template <int NT, bool CUBIC, bool EXACT>
+void eval_tensor_tiles(const DeviceModel &m, const double *q, double *out, const SortWork &w, int grid, cudaStream_t st)
+{
+	auto kern = eval_tensor_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
+	const size_t smem = (size_t)m.tl_stride * 8;
+	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	kern<<<grid, kTileQ, smem, st>>>(m, q, out, w.offset, w.tile_off, w.perm);
 }
 
 template <int NT, bool CUBIC, bool EXACT>
@@ -282,6 +318,16 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
 	const int64_t max_tiles = Q / kTileQ + m.L + 1;
 	const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)sm_count * 8);
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
+	if (m.tensor_F > 0 && m.N <= kMaxTemplateN && (size_t)m.tl_stride * 8 <= 200 * 1024) {
+#define LOCO_XCASE(NT)                                                                                                   \
+	case NT:                                                                                                             \
+		if (cubic) { if (exact) eval_tensor_tiles<NT, true, true>(m, q, out, w, grid, st); else eval_tensor_tiles<NT, true, false>(m, q, out, w, grid, st); } \
+		else { if (exact) eval_tensor_tiles<NT, false, true>(m, q, out, w, grid, st); else eval_tensor_tiles<NT, false, false>(m, q, out, w, grid, st); }     \
+		break;
+		switch (m.N) { LOCO_XCASE(1) LOCO_XCASE(2) LOCO_XCASE(3) LOCO_XCASE(4) LOCO_XCASE(5) LOCO_XCASE(6) LOCO_XCASE(7) LOCO_XCASE(8) }
+#undef LOCO_XCASE
+		return 4;
+	}
 #define LOCO_TCASE(NT)                                                                                                   \
 	case NT:                                                                                                             \
 		if (cubic) { if (exact) eval_tiles<NT, true, true>(m, q, out, w, chunk, smem, grid, st); else eval_tiles<NT, true, false>(m, q, out, w, chunk, smem, grid, st); } \

@@ -20,7 +20,7 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_vectors(golden, name, path):
     pb, z = golden(name)
