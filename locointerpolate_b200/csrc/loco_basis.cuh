@@ -43,16 +43,18 @@ __device__ __forceinline__ void map_to_cube(const DeviceModel &m, const double *
 }
 
 // LCAdaptiveGridCell::getCointainingLeaf (LCAdaptiveGridCell.cpp:260-272): strict '<' sends ties to child2.
-// One 16-byte read-only load per level; child1 is the next cell in pre-order.
+// One 16-byte read-only load per INNER level; the child codes name the leaf directly (see TreeCell).
 template <int NT>
 __device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT> &x)
 {
-	int32_t c = 0;
+	if (m.n_inner == 0) return 0;  // the root is a leaf
+	uint32_t c = 0;
 	for (;;) {
-		const int4 raw = __ldg(reinterpret_cast<const int4 *>(m.cells + c));
-		if (raw.z < 0) return raw.w;
-		const double split = __hiloint2double(raw.y, raw.x);
-		c = (x.get(raw.z) < split) ? c + 1 : raw.w;
+		const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.cells + c));
+		const double split = __hiloint2double((int)raw.y, (int)raw.x);
+		const uint32_t next = (x.get((int)(raw.z >> 28)) < split) ? (raw.z & kCodeMask) : raw.w;
+		if (next & kLeafFlag) return (int32_t)(next & (kLeafFlag - 1));
+		c = next;
 	}
 }
 

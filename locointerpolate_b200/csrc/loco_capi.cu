@@ -134,7 +134,7 @@ int build_device_model(loco_model *m)
 	if (f.L > 0x7fffffff || f.C > 0x7fffffff) return fail(m, LOCO_ERR_INVALID, "tree too large");
 	DeviceModel &dm = m->dm;
 	dm.N = f.N; dm.D = f.D; dm.basis = f.basis; dm.exact_rcp = f.exact_rcp ? 1 : 0;
-	dm.L = (int32_t)f.L; dm.C = (int32_t)f.C; dm.max_support = std::max(f.max_support, 1); dm.max_terms = f.max_terms;
+	dm.L = (int32_t)f.L; dm.C = (int32_t)f.C; dm.n_inner = (int32_t)f.cells.size(); dm.max_support = std::max(f.max_support, 1); dm.max_terms = f.max_terms;
 	dm.R = f.R;
 	dm.value_stride = f.D == 1 ? 1 : ((f.D + 1) / 2) * 2;  // rows 16-byte aligned for 128-bit loads
 	bool ok = true;

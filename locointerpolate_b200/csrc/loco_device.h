@@ -12,10 +12,10 @@ const int kMaxN = 16;          // larger N use the runtime-N instantiation (coor
 // Pointers into HBM; passed by value to every kernel.  Layout documented in DESIGN.md ("HBM layout").
 struct DeviceModel {
 	int32_t N, D, basis, exact_rcp;
-	int32_t L, C, max_support, max_terms;
+	int32_t L, C, n_inner, max_support, max_terms;
 	int64_t R, value_stride;          // rows and row stride (doubles) of the value table
 	const double *dom_min, *dom_max;  // [N]
-	const TreeCell *cells;            // [C] pre-order k-d tree, 16 B per cell
+	const TreeCell *cells;            // [n_inner] inner cells of the k-d tree in pre-order, 16 B each
 	const double *leaf_lo_eps, *leaf_hi_eps;  // [L*N]
 	const double *leaf_lo, *leaf_hi;          // [L*N]
 	const uint8_t *leaf_status;       // [L]
@@ -70,10 +70,11 @@ int launch_jitter_points(const DeviceModel &m, int64_t points_per_leaf, uint64_t
 // ---- leaf-sorted tile path (loco_tiles.cu)
 struct SortWork {
 	int32_t *count;     // [L] queries per leaf
-	int32_t *cursor;    // [L] scatter cursors
 	int32_t *offset;    // [L+1] bucket offsets
 	int32_t *tile_off;  // [L+1] tile offsets
-	int32_t *perm;      // [Q] query indices grouped by leaf
+	int32_t *rank;      // [Q] arrival rank of each query inside its leaf bucket
+	int32_t *idx;       // unused (kept for layout compatibility)
+	double *xs;         // [Q * row] sorted query records: N cube coordinates + original index, 32-byte sectors
 };
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);

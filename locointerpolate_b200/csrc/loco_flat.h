@@ -25,11 +25,15 @@ enum QueryStatus : uint8_t {
 };
 const char *status_string(int code);
 
-// one k-d tree cell as the kernels read it: one 16-byte load per level
+// One INNER k-d tree cell as the kernels read it: one 16-byte load per level.  Children are stored as
+// codes so that reaching a leaf needs no further load: code = kLeafFlag | leaf index, or the index of the
+// inner cell in `cells` (inner cells only, in pre-order).  a = (splitDirection_ << 28) | code(child1).
+const uint32_t kLeafFlag = 0x08000000u;
+const uint32_t kCodeMask = 0x0fffffffu;
 struct alignas(16) TreeCell {
-	double split;   // splitVal_
-	int32_t dim;    // splitDirection_, or -1 for a leaf
-	int32_t right;  // inner: pre-order index of child2 (child1 = index+1);  leaf: leaf index
+	double split;  // splitVal_
+	uint32_t a;    // dim << 28 | code(child1)
+	uint32_t b;    // code(child2)
 };
 
 struct Flat {
@@ -44,7 +48,7 @@ struct Flat {
 	bool exact_rcp = false;  // every support is a power of two: term_cs holds 1/s and u=(x-c)*(1/s) is bit-identical to (x-c)/s
 
 	std::vector<double> dom_min, dom_max;  // [N] ranges_[2i], ranges_[2i+1]
-	std::vector<TreeCell> cells;           // [C] pre-order
+	std::vector<TreeCell> cells;           // [#inner cells] pre-order; empty when the root is a leaf
 	std::vector<double> leaf_lo, leaf_hi;          // [L*N] leaf box
 	std::vector<double> leaf_lo_eps, leaf_hi_eps;  // [L*N] lo-EPSILON, hi+EPSILON as the reference computes them
 	std::vector<int32_t> leaf_center_row;          // [L] value row of centerShapeInfo_ (true f at the centre)

@@ -112,23 +112,32 @@ Status flatten(const Graph &g, Flat *out)
 	for (int i = 0; i < N; i++) { f.dom_min.push_back(g.domain[2 * i]); f.dom_max.push_back(g.domain[2 * i + 1]); }
 
 	// ---- tree cells, leaf numbering (getAllLeafCells order == pre-order rank of leaves) -----------
-	f.cells.resize((size_t)f.C);
 	cx.leaf_of_cell.assign((size_t)f.C, -1);
-	std::vector<int32_t> level((size_t)f.C, 0);
+	std::vector<int32_t> level((size_t)f.C, 0), inner_of_cell((size_t)f.C, -1);
+	int32_t n_inner = 0;
 	for (int64_t c = 0; c < f.C; c++) {
-		TreeCell &tc = f.cells[(size_t)c];
-		tc.dim = g.tree.split_dir[c];
-		tc.split = g.tree.split_val[c];
-		if (tc.dim < 0) {
-			tc.right = (int32_t)cx.cell_of_leaf.size();
-			cx.leaf_of_cell[(size_t)c] = tc.right;
+		if (g.tree.split_dir[c] < 0) {
+			cx.leaf_of_cell[(size_t)c] = (int32_t)cx.cell_of_leaf.size();
 			cx.cell_of_leaf.push_back((int32_t)c);
 			f.depth = std::max(f.depth, level[(size_t)c]);
 		} else {
-			tc.right = g.tree.child2[c];
+			inner_of_cell[(size_t)c] = n_inner++;
 			level[(size_t)c + 1] = level[(size_t)c] + 1;
-			level[(size_t)tc.right] = level[(size_t)c] + 1;
+			level[(size_t)g.tree.child2[c]] = level[(size_t)c] + 1;
 		}
+	}
+	if ((uint64_t)n_inner >= kLeafFlag || cx.cell_of_leaf.size() >= kLeafFlag) return Status("tree too large");
+	if (N > 16) return Status("more than 16 parameters are not supported");
+	f.cells.resize((size_t)n_inner);
+	auto code = [&](int64_t c) -> uint32_t {
+		return g.tree.split_dir[c] < 0 ? (kLeafFlag | (uint32_t)cx.leaf_of_cell[(size_t)c]) : (uint32_t)inner_of_cell[(size_t)c];
+	};
+	for (int64_t c = 0; c < f.C; c++) {
+		if (g.tree.split_dir[c] < 0) continue;
+		TreeCell &tc = f.cells[(size_t)inner_of_cell[(size_t)c]];
+		tc.split = g.tree.split_val[c];
+		tc.a = ((uint32_t)g.tree.split_dir[c] << 28) | code(c + 1);
+		tc.b = code(g.tree.child2[c]);
 	}
 	f.L = (int64_t)cx.cell_of_leaf.size();
 	const int64_t L = f.L;

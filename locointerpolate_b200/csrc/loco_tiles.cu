@@ -8,10 +8,12 @@
 // reads -- no divergence, no per-thread gathers.  Results are scattered back to the caller's order, so the
 // output does not depend on the (non-deterministic) order inside a leaf bucket.
 //
-//   1. locate_count   map -> descend -> containment; leaf[], status[]; histogram of leaves (REDG atomics)
+//   1. locate_count   map -> descend -> containment; leaf[], status[]; rank[i] = histogram[leaf]++ (one atomic per query)
 //   2. scan           exclusive scan of the histogram -> bucket offsets and tile offsets (one CTA)
-//   3. scatter        perm[offset[leaf] + cursor[leaf]++] = query index
-//   4. eval_tiles     persistent CTAs over contiguous tile ranges; terms via TMA bulk copies
+//   3. scatter        pos = offset[leaf] + rank: xs[pos] = cube coordinates, idx[pos] = query index
+//                     (random 8N-byte WRITES are cheaper than the random reads a gather in step 4 would need:
+//                     a missed read pulls a whole 128 B line from HBM, a masked write only its sectors)
+//   4. eval_tiles     persistent CTAs over contiguous tile ranges; coalesced xs/idx; leaf data via TMA bulk copies
 //
 // Reference semantics: identical to the direct path (see loco_kernels.cu); for D == 1 the per-term
 // weight and the sample value are pre-multiplied (term_wv = weight_ * val), which only re-associates
@@ -24,23 +26,63 @@
 
 namespace loco {
 
+// Sorted query record: N cube coordinates followed by the original query index, padded to whole 32-byte
+// sectors and written with 256-bit stores, so that the random scatter only ever writes FULL sectors (a
+// partial-sector write makes the L2 fetch the rest of the sector from HBM first).
+__host__ __device__ inline int sorted_row_doubles(int N) { return ((N * 8 + 4 + 31) / 32) * 4; }
+__device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
+{
+	asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_sector(const double *p, double &a, double &b, double &c, double &d)
+{
+	asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+template <int NT>
+__device__ __forceinline__ void store_sorted_row(double *row, const Coord<NT> &x, int32_t qi, int N)
+{
+	const int RS = sorted_row_doubles(N);
+	double v[(NT > 0 ? ((NT * 8 + 4 + 31) / 32) * 4 : ((kMaxN * 8 + 4 + 31) / 32) * 4)];
+#pragma unroll
+	for (int d = 0; d < RS; d++) v[d] = d < N ? x.get(d) : 0.0;
+	v[RS - 1] = __longlong_as_double((long long)qi);
+#pragma unroll
+	for (int d = 0; d < RS; d += 4) st_sector(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
+}
+template <int NT>
+__device__ __forceinline__ int32_t load_sorted_row(const double *row, Coord<NT> &x, int N)
+{
+	const int RS = sorted_row_doubles(N);
+	double v[(NT > 0 ? ((NT * 8 + 4 + 31) / 32) * 4 : ((kMaxN * 8 + 4 + 31) / 32) * 4)];
+#pragma unroll
+	for (int d = 0; d < RS; d += 4) ld_sector(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
+#pragma unroll
+	for (int d = 0; d < N; d++) x.set(d, v[d]);
+	return (int32_t)__double_as_longlong(v[RS - 1]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 1. locate + histogram
 // ---------------------------------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(256) locate_count_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
-                                                            uint8_t *__restrict__ status_out, int32_t *__restrict__ count, double *__restrict__ out)
+                                                            uint8_t *__restrict__ status_out, int32_t *__restrict__ count, int32_t *__restrict__ rank,
+                                                            double *__restrict__ out)
 {
 	const int N = NT > 0 ? NT : m.N;
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= Q) return;
 	Coord<NT> x;
-	map_to_cube<NT>(m, q + i * N, x);
+	double p[NT > 0 ? NT : kMaxN];
+	// the query stream is read exactly once here: keep it out of the way of the tree cells in L1
+#pragma unroll
+	for (int d = 0; d < N; d++) p[d] = __ldcs(q + i * N + d);
+	map_to_cube<NT>(m, p, x);
 	const int32_t leaf = descend<NT>(m, x);
 	const uint8_t st = located_status<NT>(m, x, leaf);
-	leaf_out[i] = leaf;
+	__stcs(leaf_out + i, leaf);
 	status_out[i] = st;
-	if (st == ST_OK) atomicAdd(count + leaf, 1);
+	if (st == ST_OK) __stcs(rank + i, atomicAdd(count + leaf, 1));
 	else out[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
@@ -87,24 +129,33 @@ __global__ void __launch_bounds__(1024) scan_leaves_kernel(const int32_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 3. scatter query indices into their leaf buckets
+// 3. scatter queries (as cube coordinates) and their indices into the leaf buckets
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) scatter_kernel(const int32_t *__restrict__ leaf, const uint8_t *__restrict__ status, int64_t Q,
-                                                       const int32_t *__restrict__ offset, int32_t *__restrict__ cursor, int32_t *__restrict__ perm)
+template <int NT>
+__global__ void __launch_bounds__(256) scatter_kernel(DeviceModel m, const double *__restrict__ q, const int32_t *__restrict__ leaf,
+                                                       const uint8_t *__restrict__ status, const int32_t *__restrict__ rank, int64_t Q,
+                                                       const int32_t *__restrict__ offset, int32_t *__restrict__ idx, double *__restrict__ xs)
 {
+	const int N = NT > 0 ? NT : m.N;
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= Q || status[i] != ST_OK) return;
-	const int32_t l = leaf[i];
-	perm[offset[l] + atomicAdd(cursor + l, 1)] = (int32_t)i;
+	const int64_t pos = (int64_t)__ldg(offset + __ldcs(leaf + i)) + __ldcs(rank + i);
+	double p[NT > 0 ? NT : kMaxN];
+#pragma unroll
+	for (int d = 0; d < N; d++) p[d] = __ldcs(q + i * N + d);
+	Coord<NT> x;
+	map_to_cube<NT>(m, p, x);  // same operations as in locate_count: bit-identical coordinates
+	store_sorted_row<NT>(xs + pos * sorted_row_doubles(N), x, (int32_t)i, N);
+	(void)idx;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // 4. evaluation over leaf tiles
 // ---------------------------------------------------------------------------------------------------
 template <int NT, bool CUBIC, bool EXACT, int TILE_Q>
-__global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const double *__restrict__ q, double *__restrict__ out,
+__global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const double *__restrict__ xs, double *__restrict__ out,
                                                              const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off,
-                                                             const int32_t *__restrict__ perm, int32_t chunk_terms)
+                                                             const int32_t *__restrict__ idx, int32_t chunk_terms)
 {
 	const int N = NT > 0 ? NT : m.N;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -140,8 +191,7 @@ __global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const
 		int32_t qi = 0;
 		Coord<NT> x;
 		if (active) {
-			qi = __ldg(perm + pos);
-			map_to_cube<NT>(m, q + (int64_t)qi * N, x);
+			qi = load_sorted_row<NT>(xs + (int64_t)pos * sorted_row_doubles(N), x, N);
 		} else {
 #pragma unroll
 			for (int d = 0; d < (NT > 0 ? NT : 1); d++) x.set(d, 0.0);
@@ -177,58 +227,96 @@ __global__ void __launch_bounds__(TILE_Q) eval_tiles_kernel(DeviceModel m, const
 // Tensor-product leaves: the leaf's block (centres, supports, F^N sample values in tensor order) is one
 // contiguous run of tl_stride doubles -> ONE TMA bulk copy per leaf; each thread then needs N*F
 // one-dimensional basis evaluations and a sum-factorised contraction over shared memory.
+// position of a tile in the sorted order: its leaf and query range (tiles of one leaf are consecutive)
+struct TileCursor {
+	int32_t leaf = -1, tile0 = 0, tile1 = 0;
+	__device__ __forceinline__ void seek(int64_t tile, const int32_t *__restrict__ tile_off, int32_t L)
+	{
+		if (tile < tile1) return;
+		// last leaf whose first tile is <= tile (leaves without queries own no tiles and are skipped)
+		int32_t lo = leaf < 0 ? 0 : leaf + 1, hi = L;
+		while (lo < hi) {
+			const int32_t mid = (lo + hi) >> 1;
+			if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
+		}
+		leaf = lo;
+		tile0 = __ldg(tile_off + leaf);
+		tile1 = __ldg(tile_off + leaf + 1);
+	}
+};
+
 template <int NT, bool CUBIC, bool EXACT, int TILE_Q>
-__global__ void __launch_bounds__(TILE_Q) eval_tensor_tiles_kernel(DeviceModel m, const double *__restrict__ q, double *__restrict__ out,
+__global__ void __launch_bounds__(TILE_Q) eval_tensor_tiles_kernel(DeviceModel m, const double *__restrict__ xs, double *__restrict__ out,
                                                                     const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off,
-                                                                    const int32_t *__restrict__ perm)
+                                                                    const int32_t *__restrict__ idx)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	double *s_blk = reinterpret_cast<double *>(smem_raw);  // [tl_stride]
-	__shared__ __align__(8) uint64_t bar;
-	if (threadIdx.x == 0) mbar_init(&bar, 1);
+	// two leaf blocks: the block of the NEXT tile's leaf is fetched by the TMA engine while this tile computes
+	double *const s_base = reinterpret_cast<double *>(smem_raw);
+#define S_BLK(b) (s_base + (b) * m.tl_stride)
+	__shared__ __align__(8) uint64_t bar[2];
+	if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
 	__syncthreads();
-	uint32_t phase = 0;
+	uint32_t phases = 0;  // bit b = parity to wait for on bar[b]
 	const int32_t L = m.L;
 	const int64_t total = tile_off[L];
 	const int64_t t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
-	int32_t leaf = -1, leaf_tile0 = 0, leaf_tile1 = 0, staged_leaf = -1;
-	for (int64_t tile = t_begin; tile < t_end; tile++) {
-		if (tile >= leaf_tile1) {
-			int32_t lo = leaf < 0 ? 0 : leaf + 1, hi = L;
-			while (lo < hi) {
-				const int32_t mid = (lo + hi) >> 1;
-				if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
-			}
-			leaf = lo;
-			leaf_tile0 = __ldg(tile_off + leaf);
-			leaf_tile1 = __ldg(tile_off + leaf + 1);
-		}
-		const int32_t qbeg = __ldg(offset + leaf) + (int32_t)(tile - leaf_tile0) * TILE_Q;
-		const int32_t qend = min(qbeg + TILE_Q, __ldg(offset + leaf + 1));
-		const int32_t pos = qbeg + threadIdx.x;
-		const bool active = pos < qend;
-		int32_t qi = 0;
-		Coord<NT> x;
-#pragma unroll
-		for (int d = 0; d < NT; d++) x.set(d, 0.0);
-		if (active) {
-			qi = __ldg(perm + pos);
-			map_to_cube<NT>(m, q + (int64_t)qi * NT, x);
-		}
-		if (staged_leaf != leaf) {
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				const uint32_t bytes = (uint32_t)m.tl_stride * 8;
-				mbar_expect_tx(&bar, bytes);
-				tma_bulk_g2s(s_blk, m.tl_block + (int64_t)leaf * m.tl_stride, bytes, &bar);
-			}
-			mbar_wait(&bar, phase);
-			phase ^= 1;
-			staged_leaf = leaf;
-		}
-		const double r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, s_blk, x);
-		if (active) out[qi] = r;
+	if (t_begin >= t_end) return;
+	constexpr int RS = ((NT * 8 + 4 + 31) / 32) * 4;
+	const uint32_t blk_bytes = (uint32_t)m.tl_stride * 8;
+
+	TileCursor cur;
+	// prologue: records and leaf block of the first tile
+	cur.seek(t_begin, tile_off, L);
+	int buf = 0;
+	if (threadIdx.x == 0) {
+		mbar_expect_tx(&bar[0], blk_bytes);
+		tma_bulk_g2s(S_BLK(0), m.tl_block + (int64_t)cur.leaf * m.tl_stride, blk_bytes, &bar[0]);
 	}
+	int32_t n_leaf = cur.leaf;
+	int32_t n_qbeg = __ldg(offset + cur.leaf) + (int32_t)(t_begin - cur.tile0) * TILE_Q;
+	int32_t n_qend = min(n_qbeg + TILE_Q, __ldg(offset + cur.leaf + 1));
+	Coord<NT> nx;
+	int32_t nqi = 0;
+#pragma unroll
+	for (int d = 0; d < NT; d++) nx.set(d, 0.0);
+	if (n_qbeg + (int)threadIdx.x < n_qend) nqi = load_sorted_row<NT>(xs + (int64_t)(n_qbeg + threadIdx.x) * RS, nx, NT);
+	bool need_wait = true;  // the current buffer has a copy in flight
+
+	for (int64_t tile = t_begin; tile < t_end; tile++) {
+		const Coord<NT> x = nx;
+		const int32_t qi = nqi, leaf = n_leaf;
+		const bool active = n_qbeg + (int)threadIdx.x < n_qend;
+		// ---- look ahead: next tile's records (and its leaf block if the leaf changes)
+		bool next_changes = false;
+		if (tile + 1 < t_end) {
+			cur.seek(tile + 1, tile_off, L);
+			next_changes = cur.leaf != leaf;
+			n_leaf = cur.leaf;
+			n_qbeg = __ldg(offset + cur.leaf) + (int32_t)(tile + 1 - cur.tile0) * TILE_Q;
+			n_qend = min(n_qbeg + TILE_Q, __ldg(offset + cur.leaf + 1));
+			if (next_changes && threadIdx.x == 0) {
+				// the other buffer was last read two leaves ago; every thread has passed the __syncthreads that
+				// followed that leaf, so it is free
+				mbar_expect_tx(&bar[buf ^ 1], blk_bytes);
+				tma_bulk_g2s(S_BLK(buf ^ 1), m.tl_block + (int64_t)n_leaf * m.tl_stride, blk_bytes, &bar[buf ^ 1]);
+			}
+#pragma unroll
+			for (int d = 0; d < NT; d++) nx.set(d, 0.0);
+			nqi = 0;
+			if (n_qbeg + (int)threadIdx.x < n_qend) nqi = load_sorted_row<NT>(xs + (int64_t)(n_qbeg + threadIdx.x) * RS, nx, NT);
+		}
+		// ---- this tile
+		if (need_wait) { mbar_wait(&bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; need_wait = false; }
+		const double r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, S_BLK(buf), x);
+		if (active) out[qi] = r;
+		if (next_changes) {
+			__syncthreads();  // all reads of s_blk[buf] are done before it can be refilled (two leaves from now)
+			buf ^= 1;
+			need_wait = true;
+		}
+	}
+#undef S_BLK
 }
 
 // term_wv[t] = term_w[t] * values[term_row[t]]   (scalar functions; refreshed whenever the value table changes)
@@ -242,34 +330,40 @@ __global__ void term_wv_kernel(DeviceModel m, double *__restrict__ term_wv, int6
 // launchers
 // ---------------------------------------------------------------------------------------------------
 namespace {
-const int kTileQ = 256;
+const int kTileQ = 128;
 
 template <int NT>
-void locate_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, int32_t *count, double *out, cudaStream_t st)
+void locate_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, double *out, cudaStream_t st)
 {
-	locate_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, count, out);
+	locate_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, w.count, w.rank, out);
+}
+template <int NT>
+void scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortWork &w, cudaStream_t st)
+{
+	scatter_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, leaf, status, w.rank, Q, w.offset, w.idx, w.xs);
 }
 
 template <int NT, bool CUBIC, bool EXACT>
 void eval_tensor_tiles(const DeviceModel &m, const double *q, double *out, const SortWork &w, int grid, cudaStream_t st)
 {
 	auto kern = eval_tensor_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
-	const size_t smem = (size_t)m.tl_stride * 8;
+	const size_t smem = (size_t)m.tl_stride * 8 * 2;
 	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	kern<<<grid, kTileQ, smem, st>>>(m, q, out, w.offset, w.tile_off, w.perm);
+	kern<<<grid, kTileQ, smem, st>>>(m, w.xs, out, w.offset, w.tile_off, w.idx);
 }
 
 template <int NT, bool CUBIC, bool EXACT>
 void eval_tiles(const DeviceModel &m, const double *q, double *out, const SortWork &w, int chunk_terms, size_t smem, int grid, cudaStream_t st)
 {
 	auto kern = eval_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
-	kern<<<grid, kTileQ, smem, st>>>(m, q, out, w.offset, w.tile_off, w.perm, chunk_terms);
+	kern<<<grid, kTileQ, smem, st>>>(m, w.xs, out, w.offset, w.tile_off, w.idx, chunk_terms);
 }
 } // namespace
 
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q)
 {
-	return ((size_t)m.L * 2 + (size_t)(m.L + 1) * 2 + (size_t)Q) * sizeof(int32_t) + 256;
+	const size_t ints = (size_t)m.L + (size_t)(m.L + 1) * 2 + (size_t)Q;
+	return ((ints * sizeof(int32_t) + 127) & ~(size_t)127) + (size_t)Q * sorted_row_doubles(m.N) * sizeof(double) + 256;
 }
 
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base)
@@ -277,11 +371,12 @@ SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base)
 	SortWork w;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
 	w.count = p; p += m.L;
-	w.cursor = p; p += m.L;
 	w.offset = p; p += m.L + 1;
 	w.tile_off = p; p += m.L + 1;
-	w.perm = p;
-	(void)Q;
+	w.rank = p; p += Q;
+	w.idx = nullptr;  // the index travels in the last slot of each sorted row
+	const size_t ints = (size_t)(p - reinterpret_cast<int32_t *>(base));
+	w.xs = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(base) + ((ints * sizeof(int32_t) + 127) & ~(size_t)127));
 	return w;
 }
 
@@ -296,29 +391,41 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
                              int sm_count, cudaStream_t st)
 {
 	if (Q <= 0) return 0;
-	cudaMemsetAsync(w.count, 0, (size_t)m.L * 2 * sizeof(int32_t), st);  // count and cursor are adjacent
+	cudaMemsetAsync(w.count, 0, (size_t)m.L * sizeof(int32_t), st);
+#define LOCO_SCASE(NT, FN) case NT: FN<NT>
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
-	case 1: locate_count<1>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 2: locate_count<2>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 3: locate_count<3>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 4: locate_count<4>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 5: locate_count<5>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 6: locate_count<6>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 7: locate_count<7>(m, q, Q, leaf, status, w.count, out, st); break;
-	case 8: locate_count<8>(m, q, Q, leaf, status, w.count, out, st); break;
-	default: locate_count<0>(m, q, Q, leaf, status, w.count, out, st); break;
+	case 1: locate_count<1>(m, q, Q, leaf, status, w, out, st); break;
+	case 2: locate_count<2>(m, q, Q, leaf, status, w, out, st); break;
+	case 3: locate_count<3>(m, q, Q, leaf, status, w, out, st); break;
+	case 4: locate_count<4>(m, q, Q, leaf, status, w, out, st); break;
+	case 5: locate_count<5>(m, q, Q, leaf, status, w, out, st); break;
+	case 6: locate_count<6>(m, q, Q, leaf, status, w, out, st); break;
+	case 7: locate_count<7>(m, q, Q, leaf, status, w, out, st); break;
+	case 8: locate_count<8>(m, q, Q, leaf, status, w, out, st); break;
+	default: locate_count<0>(m, q, Q, leaf, status, w, out, st); break;
 	}
 	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, kTileQ, w.offset, w.tile_off);
-	scatter_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(leaf, status, Q, w.offset, w.cursor, w.perm);
+	switch (m.N <= kMaxTemplateN ? m.N : 0) {
+	case 1: scatter<1>(m, q, Q, leaf, status, w, st); break;
+	case 2: scatter<2>(m, q, Q, leaf, status, w, st); break;
+	case 3: scatter<3>(m, q, Q, leaf, status, w, st); break;
+	case 4: scatter<4>(m, q, Q, leaf, status, w, st); break;
+	case 5: scatter<5>(m, q, Q, leaf, status, w, st); break;
+	case 6: scatter<6>(m, q, Q, leaf, status, w, st); break;
+	case 7: scatter<7>(m, q, Q, leaf, status, w, st); break;
+	case 8: scatter<8>(m, q, Q, leaf, status, w, st); break;
+	default: scatter<0>(m, q, Q, leaf, status, w, st); break;
+	}
+#undef LOCO_SCASE
 
 	const int per_term = 2 * m.N * 8 + 8;
 	int chunk = (40 * 1024) / per_term;
 	chunk = std::max(2, std::min(chunk & ~1, (m.max_terms + 1) & ~1));
 	const size_t smem = (size_t)chunk * 2 * m.N * 8 + (size_t)(chunk + 2) * 8;
 	const int64_t max_tiles = Q / kTileQ + m.L + 1;
-	const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)sm_count * 8);
+	const int grid = (int)std::min<int64_t>(max_tiles, (int64_t)sm_count * 16);
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
-	if (m.tensor_F > 0 && m.N <= kMaxTemplateN && (size_t)m.tl_stride * 8 <= 200 * 1024) {
+	if (m.tensor_F > 0 && m.N <= kMaxTemplateN && (size_t)m.tl_stride * 16 <= 200 * 1024) {
 #define LOCO_XCASE(NT)                                                                                                   \
 	case NT:                                                                                                             \
 		if (cubic) { if (exact) eval_tensor_tiles<NT, true, true>(m, q, out, w, grid, st); else eval_tensor_tiles<NT, true, false>(m, q, out, w, grid, st); } \
