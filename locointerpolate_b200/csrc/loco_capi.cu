@@ -244,7 +244,19 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		CUDA_OK(m, cudaGetLastError());
 		return LOCO_OK;
 	}
-	// mesh-valued: weights, then the weighted gather-sum, in chunks that bound the weight scratch
+	// mesh-valued on tensor-product leaves: sort by leaf, then the tiled gather-sum kernel (loco_mesh.cu)
+	if (dm.tensor_F > 0 && !in_cube && m->opt_path != 1 && m->opt_path != 3) {
+		int rc;
+		if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+		if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+		if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
+		const SortWork sw = carve_sort_work(dm, Q, w.misc);
+		m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_tile_queries(), nullptr, st);
+		m->launches += launch_mesh_tensor_tiles(dm, sw, status, Q, out, out_stride, m->sm_count, st);
+		CUDA_OK(m, cudaGetLastError());
+		return LOCO_OK;
+	}
+	// generic mesh-valued path: weights, then the weighted gather-sum, in chunks that bound the weight scratch
 	const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(Q, ((int64_t)256 << 20) / ((int64_t)dm.max_support * 8)));
 	int rc;
 	if ((rc = grow(m, &w.W, &w.W_b, (size_t)chunk * dm.max_support * sizeof(double)))) return rc;

@@ -82,6 +82,11 @@ int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cuda
 int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);
+int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, int tile_q,
+                        double *scalar_out, cudaStream_t st);
+int mesh_tile_queries();
+int launch_mesh_tensor_tiles(const DeviceModel &m, const SortWork &w, const uint8_t *status, int64_t Q, double *out, int64_t out_stride, int sm_count,
+                             cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
 

@@ -22,44 +22,10 @@
 
 #include "loco_basis.cuh"
 #include "loco_device.h"
+#include "loco_sort.cuh"
 #include "loco_tma.cuh"
 
 namespace loco {
-
-// Sorted query record: N cube coordinates followed by the original query index, padded to whole 32-byte
-// sectors and written with 256-bit stores, so that the random scatter only ever writes FULL sectors (a
-// partial-sector write makes the L2 fetch the rest of the sector from HBM first).
-__host__ __device__ inline int sorted_row_doubles(int N) { return ((N * 8 + 4 + 31) / 32) * 4; }
-__device__ __forceinline__ void st_sector(double *p, double a, double b, double c, double d)
-{
-	asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ void ld_sector(const double *p, double &a, double &b, double &c, double &d)
-{
-	asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-template <int NT>
-__device__ __forceinline__ void store_sorted_row(double *row, const Coord<NT> &x, int32_t qi, int N)
-{
-	const int RS = sorted_row_doubles(N);
-	double v[(NT > 0 ? ((NT * 8 + 4 + 31) / 32) * 4 : ((kMaxN * 8 + 4 + 31) / 32) * 4)];
-#pragma unroll
-	for (int d = 0; d < RS; d++) v[d] = d < N ? x.get(d) : 0.0;
-	v[RS - 1] = __longlong_as_double((long long)qi);
-#pragma unroll
-	for (int d = 0; d < RS; d += 4) st_sector(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
-}
-template <int NT>
-__device__ __forceinline__ int32_t load_sorted_row(const double *row, Coord<NT> &x, int N)
-{
-	const int RS = sorted_row_doubles(N);
-	double v[(NT > 0 ? ((NT * 8 + 4 + 31) / 32) * 4 : ((kMaxN * 8 + 4 + 31) / 32) * 4)];
-#pragma unroll
-	for (int d = 0; d < RS; d += 4) ld_sector(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
-#pragma unroll
-	for (int d = 0; d < N; d++) x.set(d, v[d]);
-	return (int32_t)__double_as_longlong(v[RS - 1]);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // 1. locate + histogram
@@ -83,7 +49,7 @@ __global__ void __launch_bounds__(256) locate_count_kernel(DeviceModel m, const 
 	__stcs(leaf_out + i, leaf);
 	status_out[i] = st;
 	if (st == ST_OK) __stcs(rank + i, atomicAdd(count + leaf, 1));
-	else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+	else if (out) out[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -387,12 +353,12 @@ int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cuda
 	return 1;
 }
 
-int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
-                             int sm_count, cudaStream_t st)
+// steps 1-3: leaf[], status[], and the queries as sorted records (w.xs) with bucket / tile offsets for tiles of tile_q
+int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, int tile_q,
+                        double *scalar_out, cudaStream_t st)
 {
-	if (Q <= 0) return 0;
+	double *out = scalar_out;
 	cudaMemsetAsync(w.count, 0, (size_t)m.L * sizeof(int32_t), st);
-#define LOCO_SCASE(NT, FN) case NT: FN<NT>
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 	case 1: locate_count<1>(m, q, Q, leaf, status, w, out, st); break;
 	case 2: locate_count<2>(m, q, Q, leaf, status, w, out, st); break;
@@ -404,7 +370,7 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
 	case 8: locate_count<8>(m, q, Q, leaf, status, w, out, st); break;
 	default: locate_count<0>(m, q, Q, leaf, status, w, out, st); break;
 	}
-	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, kTileQ, w.offset, w.tile_off);
+	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, tile_q, w.offset, w.tile_off);
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 	case 1: scatter<1>(m, q, Q, leaf, status, w, st); break;
 	case 2: scatter<2>(m, q, Q, leaf, status, w, st); break;
@@ -416,7 +382,14 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
 	case 8: scatter<8>(m, q, Q, leaf, status, w, st); break;
 	default: scatter<0>(m, q, Q, leaf, status, w, st); break;
 	}
-#undef LOCO_SCASE
+	return 3;
+}
+
+int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
+                             int sm_count, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	launch_sort_by_leaf(m, q, Q, leaf, status, w, kTileQ, out, st);
 
 	const int per_term = 2 * m.N * 8 + 8;
 	int chunk = (40 * 1024) / per_term;

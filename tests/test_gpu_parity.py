@@ -69,7 +69,7 @@ def test_device_buffers_and_ragged_sizes(golden, name):
         assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("name,D", [("c1_lin2d_boot2", 6), ("cub2d_adapt6", 7), ("cub3d_boot2", 30), ("lin4d_boot1", 300)])
+@pytest.mark.parametrize("name,D", [("c1_lin2d_boot2", 6), ("cub2d_adapt6", 7), ("cub2d_boot2", 5), ("cub3d_boot2", 30), ("cub3d_boot1_nocorner", 131), ("lin4d_boot1", 300)])
 def test_mesh_valued(golden, name, D):
     """D > 1: per-vertex mesh vectors.  Oracle = LCRealFunctionValue::add applied component-wise."""
     pb, z = golden(name)
