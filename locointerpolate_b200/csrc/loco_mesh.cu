@@ -90,20 +90,25 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mesh_tensor_tiles_kernel(Device
 		}
 		__syncthreads();
 
-		for (int32_t dchunk = (int32_t)dgroup * MT_DG; dchunk < min((int32_t)(dgroup + 1) * MT_DG, n_dchunks); dchunk++) {
-		const int32_t d0 = dchunk * MT_D;
-		const int32_t nd = min(MT_D, m.D - d0);
-		const uint32_t row_bytes = (uint32_t)(((nd + 1) & ~1) * 8);  // value rows are padded to an even number of doubles
-		auto issue_stage = [&](int c, int b) {
+		// ---- flat sequence of steps = (component chunk, row stage); the TMA copies and the weights of step s+1
+		//      are produced while step s computes, across chunk boundaries too
+		const int32_t dc0 = (int32_t)dgroup * MT_DG;
+		const int n_dc = min(MT_DG, n_dchunks - dc0);
+		const int n_steps = n_dc * n_stages;
+		// issued by warp 0: lane 0 arms the barrier, then every lane starts the copy of one value row segment
+		auto issue_step = [&](int s) {
+			const int dc = s / n_stages, c = s - dc * n_stages, b = s & 1;
+			const int32_t d0 = (dc0 + dc) * MT_D;
+			const uint32_t row_bytes = (uint32_t)(((min(MT_D, m.D - d0) + 1) & ~1) * 8);  // rows are padded to an even number of doubles
 			const int kc = min(MT_K, K - c * MT_K);
-			mbar_expect_tx(&bar[b], row_bytes * (uint32_t)kc);
-			for (int kk = 0; kk < kc; kk++)
-				tma_bulk_g2s(sV + ((size_t)b * MT_K + kk) * MT_D, m.values + (int64_t)__ldg(rows + c * MT_K + kk) * m.value_stride + d0, row_bytes, &bar[b]);
+			if (td == 0) mbar_expect_tx(&bar[b], row_bytes * (uint32_t)kc);
+			__syncwarp();
+			if (td < kc)
+				tma_bulk_g2s(sV + ((size_t)b * MT_K + td) * MT_D, m.values + (int64_t)__ldg(rows + c * MT_K + td) * m.value_stride + d0, row_bytes, &bar[b]);
 		};
-		if (threadIdx.x == 0) issue_stage(0, 0);
-
-		// weights of stage c into sW[b]: w[kk][q] = prod_d sF[d*F + j_d(k)][q], k = c*MT_K + kk, dimension 0 fastest
-		auto make_weights = [&](int c, int b) {
+		// weights of a step into sW[b]: w[kk][q] = prod_d sF[d*F + j_d(k)][q], k = c*MT_K + kk, dimension 0 fastest
+		auto make_weights = [&](int s) {
+			const int c = s % n_stages, b = s & 1;
 			const int kc = min(MT_K, K - c * MT_K);
 			for (int e = threadIdx.x; e < kc * MT_Q; e += MT_THREADS) {
 				const int kk = e / MT_Q, q = e - kk * MT_Q;
@@ -117,20 +122,22 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mesh_tensor_tiles_kernel(Device
 				sW[((size_t)b * MT_K + kk) * MT_Q + q] = w;
 			}
 		};
-		make_weights(0, 0);
+		if (tq == 0) issue_step(0);
+		make_weights(0);
 		__syncthreads();
 
 		double acc[8][4];
+		for (int s = 0; s < n_steps; s++) {
+			const int dc = s / n_stages, c = s - dc * n_stages, b = s & 1;
+			if (s + 1 < n_steps) {
+				if (tq == 0) issue_step(s + 1);  // buffer b^1 was released by the barrier that ended step s-1
+				make_weights(s + 1);
+			}
+			if (c == 0) {
 #pragma unroll
-		for (int i = 0; i < 8; i++)
+				for (int i = 0; i < 8; i++)
 #pragma unroll
-			for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-
-		for (int c = 0; c < n_stages; c++) {
-			const int b = c & 1;
-			if (c + 1 < n_stages) {
-				if (threadIdx.x == 0) issue_stage(c + 1, b ^ 1);  // buffer b^1 was released by the barrier that ended stage c-1
-				make_weights(c + 1, b ^ 1);
+					for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
 			}
 			mbar_wait(&bar[b], (phases >> b) & 1u);
 			phases ^= 1u << b;
@@ -154,28 +161,28 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mesh_tensor_tiles_kernel(Device
 					acc[i][3] = fma(w[i], vb.y, acc[i][3]);
 				}
 			}
-			__syncthreads();  // sV[b], sW[b] free again; sW[b^1] of the next stage visible
-		}
-
-		// ---- epilogue: each output element is written exactly once, 16-byte stores where alignment allows
+			if (c == n_stages - 1) {
+				// ---- epilogue of a chunk: each output element is written exactly once, 16-byte stores where alignment allows
+				const int32_t d0 = (dc0 + dc) * MT_D;
+				const int32_t nd = min(MT_D, m.D - d0);
 #pragma unroll
-		for (int i = 0; i < 8; i++) {
-			const int q = tq * 8 + i;
-			const int32_t qi = sQi[q];
-			if (qi < 0) continue;
-			double *o = out + (int64_t)qi * out_stride + d0;
+				for (int i = 0; i < 8; i++) {
+					const int32_t qi = sQi[tq * 8 + i];
+					if (qi < 0) continue;
+					double *o = out + (int64_t)qi * out_stride + d0;
 #pragma unroll
-			for (int h = 0; h < 2; h++) {
-				const int col = td * 2 + 64 * h;
-				if (vec_out && col + 1 < nd) {
-					*reinterpret_cast<double2 *>(o + col) = make_double2(acc[i][2 * h], acc[i][2 * h + 1]);
-				} else {
-					if (col < nd) o[col] = acc[i][2 * h];
-					if (col + 1 < nd) o[col + 1] = acc[i][2 * h + 1];
+					for (int h = 0; h < 2; h++) {
+						const int col = td * 2 + 64 * h;
+						if (vec_out && col + 1 < nd) {
+							__stcs(reinterpret_cast<double2 *>(o + col), make_double2(acc[i][2 * h], acc[i][2 * h + 1]));
+						} else {
+							if (col < nd) o[col] = acc[i][2 * h];
+							if (col + 1 < nd) o[col + 1] = acc[i][2 * h + 1];
+						}
+					}
 				}
 			}
-		}
-		__syncthreads();  // sV / sW are rewritten by the next chunk, sQi / sF by the next item
+			__syncthreads();  // sV[b], sW[b] free again; sW[b^1] of the next step visible; after the last step: sQi / sF free
 		}
 	}
 }
