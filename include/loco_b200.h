@@ -127,6 +127,12 @@ int loco_model_info(const loco_model_t *m, loco_info_t *info);
  * (LCAdaptiveGridCell.cpp:558-607).  *k receives the count; LOCO_ERR_RANGE if cap is too small. */
 int loco_support_set(const loco_model_t *m, int32_t leaf, int32_t *ids, int32_t cap, int32_t *k);
 
+/* LCSampledFunction::getMinRange/getMaxRange (LCSampledFunction.cpp:52-59): ranges [2N] = min,max per parameter */
+int loco_model_domain(const loco_model_t *m, double *ranges);
+
+/* LCAdaptiveGridCell::ranges_ of a leaf in cube coordinates: box [2N] = lo,hi per dimension (LCAdaptiveGridCell.h:89) */
+int loco_leaf_box(const loco_model_t *m, int32_t leaf, double *box);
+
 /* number of leaf / border-cell neighbours of a leaf (LCAdaptiveGridCell::getNeighbors, :93-96) */
 int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, int32_t *n_border);
 
@@ -165,6 +171,18 @@ int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t n_queries, 
  * that the results are streamed through (every output element is written to HBM exactly once). */
 int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t n_queries, double *ring, int64_t ring_queries,
                                 double *checksum, int32_t *leaf, uint8_t *status, void *cuda_stream);
+
+/* ---- derivative ------------------------------------------------------------------------------------------
+ * LCSampledFunction::evalDeriv(params, direction, &result) (LCSampledFunction.cpp:61-67) for a batch:
+ *   LCAdaptiveGridCell::evalDeriv (LCAdaptiveGridCell.cpp:678-711) -> LCSample::getDerivInterpolationWeight
+ *   (LCSample.cpp:92-105) -> LCLinearBSpline/LCCubicBSpline::evalDeriv (LCBasisFunction.cpp:295-332, 421-483)
+ *   -> LCFunctionDeriv::newFromWeightedSum (LCFunctionDeriv.cpp:12-35; LCRealFunctionValue only => D == 1).
+ * The derivative is taken along CUBE coordinate `direction`, as in the reference.  The linear basis follows the
+ * reference's formula literally, including its use of the signed distance (see loco_basis.cuh). */
+int loco_eval_deriv_batch(loco_model_t *m, const double *q, int64_t n_queries, int32_t direction, double *out, int32_t *leaf,
+                          uint8_t *status);
+int loco_eval_deriv_batch_device(loco_model_t *m, const double *q, int64_t n_queries, int32_t direction, double *out, int32_t *leaf,
+                                 uint8_t *status, void *cuda_stream);
 
 /* ---- refinement-loop error check ---------------------------------------------------------------------
  * The data-parallel part of LCAdaptiveGrid::decideSplit (LCAdaptiveGrid.cpp:578-626) with

@@ -69,6 +69,10 @@ SIGNATURES = {
     "loco_eval_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "loco_eval_batch_device": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "loco_eval_batch_ring_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "loco_model_domain": (C.c_int, [_vp, _vp]),
+    "loco_leaf_box": (C.c_int, [_vp, _i32, _vp]),
+    "loco_eval_deriv_batch": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "loco_eval_deriv_batch_device": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "loco_error_check": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, C.POINTER(_i64)]),
     "loco_error_check_device": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp]),
     "loco_center_error": (C.c_int, [_vp, _f64, _vp, _vp]),
@@ -321,6 +325,30 @@ class Model:
                          status_ptr: int = 0, stream: int = 0):
         self._check(lib().loco_eval_batch_ring_device(self._h, q_ptr, Q, ring_ptr, ring_queries, checksum_ptr, leaf_ptr or None,
                                                       status_ptr or None, stream or None))
+
+    # ---- derivative along one cube direction (scalar functions)
+    def eval_deriv(self, q, direction: int):
+        q = _np(q, np.float64).reshape(-1, self.N)
+        Q = len(q)
+        out = np.empty(Q)
+        leaf = np.empty(Q, dtype=np.int32)
+        status = np.empty(Q, dtype=np.uint8)
+        self._check(lib().loco_eval_deriv_batch(self._h, _ptr(q), Q, direction, _ptr(out), _ptr(leaf), _ptr(status)))
+        return out, leaf, status
+
+    def eval_deriv_device(self, q_ptr: int, Q: int, direction: int, out_ptr: int, leaf_ptr: int = 0, status_ptr: int = 0, stream: int = 0):
+        self._check(lib().loco_eval_deriv_batch_device(self._h, q_ptr, Q, direction, out_ptr, leaf_ptr or None, status_ptr or None, stream or None))
+
+    @property
+    def domain(self) -> np.ndarray:
+        r = np.empty(2 * self.N)
+        self._check(lib().loco_model_domain(self._h, _ptr(r)))
+        return r
+
+    def leaf_box(self, leaf: int) -> np.ndarray:
+        r = np.empty(2 * self.N)
+        self._check(lib().loco_leaf_box(self._h, leaf, _ptr(r)))
+        return r.reshape(self.N, 2)
 
     # ---- error check
     def error_check(self, q, truth, threshold: float):

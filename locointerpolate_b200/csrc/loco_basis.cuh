@@ -212,6 +212,53 @@ __device__ __forceinline__ double term_value(const double *__restrict__ cs, doub
 	return value * weight;
 }
 
+// ---- derivatives (cube coordinates) ------------------------------------------------------------------------
+// One dimension of LCLinearBSpline::evalDeriv (LCBasisFunction.cpp:295-332), restated LITERALLY: the reference
+// compares the SIGNED d = (x-c)/s with 1 (no abs), so for d < 0 a non-direction dimension yields 1-d (> 1) and
+// d < -1 is not cut off.  rs = 1/s.
+__device__ __forceinline__ double linear_1d_ref_deriv(double d, double rs, bool is_dir)
+{
+	if (!(d <= 1.0)) return 0.0;
+	if (is_dir) return d < 0.0 ? rs : (d > 0.0 ? -rs : 0.0);
+	return 1.0 - d;
+}
+// One dimension of LCCubicBSpline::evalDeriv in the derivative direction (LCBasisFunction.cpp:421-455): the
+// reference's own piecewise form, p = 2(u+1), k = floor(p), t = 1-(p-k), dt = -2/s.
+__device__ __forceinline__ double cubic_1d_deriv(double u, double rs)
+{
+	if (!(fabs(u) <= 1.0)) return 0.0;
+	const double p = 2.0 * (u + 1.0);
+	const double kf = floor(p);
+	const double t = 1.0 - (p - kf);
+	const double hdt = -rs;  // dt / 2
+	const int k = (int)kf;
+	double r = 0.0;
+	if (k == 0) r = -(1.0 - t) * (1.0 - t) * hdt;
+	else if (k == 1) r = (3.0 * t * t - 4.0 * t) * hdt;
+	else if (k == 2) r = (-3.0 * t * t + 2.0 * t + 1.0) * hdt;
+	else if (k == 3) r = t * t * hdt;
+	return r;
+}
+// LC{Linear,Cubic}BSpline::evalDeriv: product over dimensions with the derivative factor in `dir`, times weight_
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double term_deriv(const double *__restrict__ cs, double weight, const Coord<NT> &x, int dir, int Nrt)
+{
+	const int N = NT > 0 ? NT : Nrt;
+	double value = 1.0;
+#pragma unroll
+	for (int d = 0; d < N; d++) {
+		const double2 c = __ldg(reinterpret_cast<const double2 *>(cs) + d);
+		const double diff = x.get(d) - c.x;
+		const double u = EXACT ? diff * c.y : diff / c.y;
+		const double rs = EXACT ? c.y : 1.0 / c.y;
+		double f;
+		if (CUBIC) f = (d == dir) ? cubic_1d_deriv(u, rs) : cubic_1d(u);
+		else f = linear_1d_ref_deriv(u, rs, d == dir);
+		value *= f;
+	}
+	return value * weight;
+}
+
 // same as term_value with the term's (c, s) pairs in SHARED memory (broadcast reads) and the weight
 // already multiplied by the sample value
 template <int NT, bool CUBIC, bool EXACT>

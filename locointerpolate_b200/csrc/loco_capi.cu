@@ -157,6 +157,12 @@ int build_device_model(loco_model *m)
 	if ((rc = upload(m, f.term_w, &dm.term_w))) return rc;
 	if ((rc = upload(m, f.term_slot, &dm.term_slot))) return rc;
 	if ((rc = upload(m, f.term_row, &dm.term_row))) return rc;
+	std::vector<int32_t> dterm_off = narrow(m, f.dterm_off, &ok);
+	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
+	if ((rc = upload(m, dterm_off, &dm.dterm_off))) return rc;
+	if ((rc = upload(m, f.dterm_cs, &dm.dterm_cs, 2))) return rc;
+	if ((rc = upload(m, f.dterm_w, &dm.dterm_w))) return rc;
+	if ((rc = upload(m, f.dterm_row, &dm.dterm_row))) return rc;
 	// value table
 	size_t vbytes = (size_t)std::max<int64_t>(f.R, 1) * dm.value_stride * sizeof(double);
 	CUDA_OK(m, cudaMalloc((void **)&m->d_values, vbytes));
@@ -204,6 +210,9 @@ int build_device_model(loco_model *m)
 	std::vector<double>().swap(f.term_w);
 	std::vector<int32_t>().swap(f.term_slot);
 	std::vector<int32_t>().swap(f.term_row);
+	std::vector<double>().swap(f.dterm_cs);
+	std::vector<double>().swap(f.dterm_w);
+	std::vector<int32_t>().swap(f.dterm_row);
 	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamCreateWithFlags(&m->ws[s].stream, cudaStreamNonBlocking));
 	return LOCO_OK;
 }
@@ -434,6 +443,22 @@ int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, in
 	return LOCO_OK;
 }
 
+int loco_model_domain(const loco_model_t *m, double *ranges)
+{
+	if (!m || !ranges) return fail(m, LOCO_ERR_INVALID, "null argument");
+	for (int i = 0; i < m->flat.N; i++) { ranges[2 * i] = m->flat.dom_min[(size_t)i]; ranges[2 * i + 1] = m->flat.dom_max[(size_t)i]; }
+	return LOCO_OK;
+}
+
+int loco_leaf_box(const loco_model_t *m, int32_t leaf, double *box)
+{
+	if (!m || !box) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (leaf < 0 || leaf >= m->flat.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	const int N = m->flat.N;
+	for (int i = 0; i < N; i++) { box[2 * i] = m->flat.leaf_lo[(size_t)leaf * N + i]; box[2 * i + 1] = m->flat.leaf_hi[(size_t)leaf * N + i]; }
+	return LOCO_OK;
+}
+
 const char *loco_last_error(const loco_model_t *m) { return m ? m->err.c_str() : g_ctor_error.c_str(); }
 const char *loco_status_string(int status) { return status_string(status); }
 
@@ -524,6 +549,50 @@ int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t Q, dou
 		m->launches += launch_checksum(ring, dm.value_stride, dm.D, n, checksum + o, st);
 	}
 	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+// ---- derivative ---------------------------------------------------------------------------------------------------
+int loco_eval_deriv_batch_device(loco_model_t *m, const double *q, int64_t Q, int32_t direction, double *out, int32_t *leaf, uint8_t *status,
+                                 void *cuda_stream)
+{
+	if (!m || (Q > 0 && (!q || !out))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (m->flat.D != 1) return fail(m, LOCO_ERR_INVALID, "Shape info type not specified");  // LCFunctionDeriv.cpp:22-34: Real values only
+	if (direction < 0 || direction >= m->flat.N) return fail(m, LOCO_ERR_RANGE, "derivative direction out of range");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	m->launches += launch_eval_deriv_direct(m->dm, q, Q, direction, out, leaf, status, (cudaStream_t)cuda_stream);
+	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+int loco_eval_deriv_batch(loco_model_t *m, const double *q, int64_t Q, int32_t direction, double *out, int32_t *leaf, uint8_t *status)
+{
+	if (!m || (Q > 0 && (!q || !out))) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (m->flat.D != 1) return fail(m, LOCO_ERR_INVALID, "Shape info type not specified");
+	if (direction < 0 || direction >= m->flat.N) return fail(m, LOCO_ERR_RANGE, "derivative direction out of range");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	const int64_t chunk = std::min<int64_t>((int64_t)4 << 20, std::max<int64_t>(Q, 1));
+	int rc;
+	int slot = 0;
+	for (int64_t o = 0; o < Q; o += chunk, slot = (slot + 1) % kSlots) {
+		const int64_t n = std::min(chunk, Q - o);
+		Workspace &w = m->ws[slot];
+		CUDA_OK(m, cudaStreamSynchronize(w.stream));
+		if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
+		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * 8))) return rc;
+		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
+		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
+		CUDA_OK(m, cudaMemcpyAsync(w.q, q + o * dm.N, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
+		m->launches += launch_eval_deriv_direct(dm, (const double *)w.q, n, direction, (double *)w.out, (int32_t *)w.leaf, (uint8_t *)w.status, w.stream);
+		CUDA_OK(m, cudaGetLastError());
+		CUDA_OK(m, cudaMemcpyAsync(out + o, w.out, (size_t)n * 8, cudaMemcpyDeviceToHost, w.stream));
+		if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
+		if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+	}
+	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamSynchronize(m->ws[s].stream));
 	return LOCO_OK;
 }
 

@@ -29,6 +29,10 @@ struct DeviceModel {
 	const int32_t *term_row;          // [sum T]
 	const double *term_wv;            // [sum T + 2] weight * value of the owning sample (scalar functions only)
 	const double *values;             // [R * value_stride]
+	// derivative-only extra terms of the linear basis (CSR by leaf; see Flat::dterm_*)
+	const int32_t *dterm_off;
+	const double *dterm_cs, *dterm_w;
+	const int32_t *dterm_row;
 	// tensor-product leaves (tensor_F > 0): one block of tl_stride doubles per leaf,
 	//   [N*F centres | N supports-or-reciprocals | pad to even | F^N sample values in tensor order (D == 1 only)]
 	int32_t tensor_F, tensor_K, tl_stride, tl_voff;
@@ -47,6 +51,9 @@ int launch_eval_scalar_direct(const DeviceModel &m, const double *q, int64_t Q, 
 // same, but q holds CUBE coordinates and leaf[] the cell to evaluate in (evaluation on a known cell)
 int launch_eval_scalar_in_cube(const DeviceModel &m, const double *x, int64_t Q, double *out, int32_t *leaf,
                                uint8_t *status, cudaStream_t st);
+// d/dx_direction of the interpolant in CUBE coordinates (LCSampledFunction::evalDeriv), scalar functions
+int launch_eval_deriv_direct(const DeviceModel &m, const double *q, int64_t Q, int direction, double *out, int32_t *leaf,
+                             uint8_t *status, cudaStream_t st);
 // locate only: cube coordinates xs [Q*N] (may be null), leaf, status
 int launch_locate(const DeviceModel &m, const double *q, int64_t Q, double *xs, int32_t *leaf, uint8_t *status, cudaStream_t st);
 // per-sample weights of each query's leaf: W [Q * max_support] (slots beyond K are zero)

@@ -66,6 +66,13 @@ struct Flat {
 	std::vector<int32_t> term_slot;    // [sum T] position of the owning sample in the leaf's support list (ascending)
 	std::vector<int32_t> term_row;     // [sum T] = sup_row[sup_off[leaf] + slot]
 
+	// derivative-only extra terms (linear basis; see loco_flatten.cpp): hats outside the leaf that the reference's
+	// LCLinearBSpline::evalDeriv still counts because it compares the SIGNED distance with 1
+	std::vector<int64_t> dterm_off;    // [L+1]
+	std::vector<double> dterm_cs;      // [sum * 2N]
+	std::vector<double> dterm_w;       // [sum]
+	std::vector<int32_t> dterm_row;    // [sum]
+
 	std::vector<int32_t> sample_row;   // [S]
 	std::vector<double> values;        // [R*D] (may be empty when the table is filled on the device)
 

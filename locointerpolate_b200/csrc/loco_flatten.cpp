@@ -229,6 +229,7 @@ Status flatten(const Graph &g, Flat *out)
 	f.exact_rcp = true;
 	for (double s : g.bf_support) if (!is_pow2(s)) { f.exact_rcp = false; break; }
 	f.term_off.assign(1, 0);
+	f.dterm_off.assign(1, 0);
 	for (int64_t l = 0; l < L; l++) {
 		const double *lo = &f.leaf_lo_eps[(size_t)l * N], *hi = &f.leaf_hi_eps[(size_t)l * N];
 		for (int64_t k = f.sup_off[(size_t)l]; k < f.sup_off[(size_t)l + 1]; k++) {
@@ -242,7 +243,28 @@ Status flatten(const Graph &g, Flat *out)
 					double m = 1e-9 + 1e-12 * (std::fabs(c[i]) + std::fabs(sp[i]) + std::fabs(lo[i]) + std::fabs(hi[i]));
 					if ((c[i] + sp[i] < lo[i] - m) || (c[i] - sp[i] > hi[i] + m)) reach = false;
 				}
-				if (!reach) continue;
+				if (!reach) {
+					// The reference's LINEAR evalDeriv tests the SIGNED d = (x-c)/s against 1 (LCBasisFunction.cpp:295-332),
+					// so a hat lying entirely to the right of the leaf in some dimension (d < -1 there) still
+					// contributes to a derivative.  Such terms are kept in a derivative-only list; a hat entirely
+					// to the LEFT in any dimension has d > 1 there and is zero in the reference too.
+					if (!cubic) {
+						bool left = false;
+						for (int i = 0; i < N && !left; i++) {
+							double m = 1e-9 + 1e-12 * (std::fabs(c[i]) + std::fabs(sp[i]) + std::fabs(lo[i]) + std::fabs(hi[i]));
+							left = c[i] + sp[i] < lo[i] - m;
+						}
+						if (!left) {
+							for (int i = 0; i < N; i++) {
+								f.dterm_cs.push_back(c[i]);
+								f.dterm_cs.push_back(f.exact_rcp ? 1.0 / sp[i] : sp[i]);
+							}
+							f.dterm_w.push_back(g.bf_weight[b]);
+							f.dterm_row.push_back(f.sup_row[(size_t)k]);
+						}
+					}
+					continue;
+				}
 				for (int i = 0; i < N; i++) {
 					f.term_cs.push_back(c[i]);
 					f.term_cs.push_back(f.exact_rcp ? 1.0 / sp[i] : sp[i]);
@@ -253,6 +275,7 @@ Status flatten(const Graph &g, Flat *out)
 			}
 		}
 		f.term_off.push_back((int64_t)f.term_w.size());
+		f.dterm_off.push_back((int64_t)f.dterm_w.size());
 		f.max_terms = std::max<int32_t>(f.max_terms, (int32_t)(f.term_off[(size_t)l + 1] - f.term_off[(size_t)l]));
 	}
 

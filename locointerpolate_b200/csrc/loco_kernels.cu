@@ -61,6 +61,37 @@ __global__ void __launch_bounds__(256) eval_scalar_direct_kernel(DeviceModel m, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// derivative along one cube direction, one thread per query        (LCSampledFunction::evalDeriv,
+// LCSampledFunction.cpp:61-67 -> LCAdaptiveGridCell::evalDeriv :678-711 -> LCSample::getDerivInterpolationWeight
+// LCSample.cpp:92-105 -> LCFunctionDeriv::newFromWeightedSum / LCRealFunctionDeriv::add)
+// ---------------------------------------------------------------------------------------------------
+template <int NT, bool CUBIC, bool EXACT, bool UNUSED>
+__global__ void __launch_bounds__(256) eval_deriv_direct_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int direction,
+                                                                 double *__restrict__ out, int32_t *__restrict__ leaf_out,
+                                                                 uint8_t *__restrict__ status_out)
+{
+	const int N = NT > 0 ? NT : m.N;
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= Q) return;
+	Coord<NT> x;
+	map_to_cube<NT>(m, q + i * N, x);
+	const int32_t leaf = descend<NT>(m, x);
+	const uint8_t st = located_status<NT>(m, x, leaf);
+	double r = __longlong_as_double(0x7ff8000000000000LL);
+	if (st == ST_OK) {
+		r = 0.0;  // LCRealFunctionDeriv(0)
+		for (int t = m.term_off[leaf], t1 = m.term_off[leaf + 1]; t < t1; t++)
+			r += term_deriv<NT, CUBIC, EXACT>(m.term_cs + (int64_t)t * 2 * N, m.term_w[t], x, direction, N) * m.values[(int64_t)m.term_row[t] * m.value_stride];
+		if (!CUBIC)
+			for (int t = m.dterm_off[leaf], t1 = m.dterm_off[leaf + 1]; t < t1; t++)
+				r += term_deriv<NT, CUBIC, EXACT>(m.dterm_cs + (int64_t)t * 2 * N, m.dterm_w[t], x, direction, N) * m.values[(int64_t)m.dterm_row[t] * m.value_stride];
+	}
+	out[i] = r;
+	if (leaf_out) leaf_out[i] = leaf;
+	if (status_out) status_out[i] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // locate only                                                (mapToStandardHypercube + getCointainingLeaf)
 // ---------------------------------------------------------------------------------------------------
 template <int NT>
@@ -333,7 +364,21 @@ struct WeightsLauncher {
 		weights_kernel<NT, CUBIC, EXACT, IN_CUBE><<<blocks_for(Q, 256), 256, 0, st>>>(m, q, Q, W, leaf, status);
 	}
 };
+template <int NT, bool CUBIC, bool EXACT, bool UNUSED>
+struct EvalDerivLauncher {
+	static void run(const DeviceModel &m, const double *q, int64_t Q, int direction, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
+	{
+		eval_deriv_direct_kernel<NT, CUBIC, EXACT, UNUSED><<<blocks_for(Q, 256), 256, 0, st>>>(m, q, Q, direction, out, leaf, status);
+	}
+};
 } // namespace
+
+int launch_eval_deriv_direct(const DeviceModel &m, const double *q, int64_t Q, int direction, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	dispatch<EvalDerivLauncher, false>(m, q, Q, direction, out, leaf, status, st);
+	return 1;
+}
 
 int launch_eval_scalar_direct(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
 {

@@ -208,6 +208,64 @@ double interpolationWeight(const Function *f, const Sample &s, const double *pos
 	return combination;
 }
 
+// LCLinearBSpline::evalDeriv (LCBasisFunction.cpp:295-332) -- restated literally: d is the SIGNED distance
+double evalDerivLinear(const Basis &b, const double *pos, int direction, int n)
+{
+	double value = 1;
+	for (int i = 0; i < n; i++) {
+		double dimVal = 0;
+		double d = (pos[i] - b.center[i]) / b.support[i];
+		if (i == direction) {
+			if (d <= 1) {
+				if (d < 0) dimVal = 1.0 / b.support[i];
+				if (d > 0) dimVal = -1.0 / b.support[i];
+			}
+		} else {
+			if (d <= 1) dimVal = 1 - d;
+		}
+		value *= dimVal;
+	}
+	return value * b.weight;
+}
+
+// LCCubicBSpline::evalDeriv (LCBasisFunction.cpp:421-483)
+double evalDerivCubic(const Basis &b, const double *pos, int direction, int n)
+{
+	double value = 1;
+	for (int i = 0; i < n; i++) {
+		double dimVal = 0;
+		double d = std::fabs(pos[i] - b.center[i]) / b.support[i];
+		if (d <= 1) {
+			double p = 2 * ((pos[i] - b.center[i]) / b.support[i] + 1);
+			int k = (int)std::floor(p);
+			double t = 1 - (p - k);
+			if (i == direction) {
+				double dt = -2 / b.support[i];
+				if (k == 0) dimVal = -(1 - t) * (1 - t) * dt / 2;
+				if (k == 1) dimVal = (3 * t * t - 4 * t) * dt / 2;
+				if (k == 2) dimVal = (-3 * t * t + 2 * t + 1) * dt / 2;
+				if (k == 3) dimVal = t * t * dt / 2;
+			} else {
+				if (k == 0) dimVal = (1 - t) * (1 - t) * (1 - t) / 6;
+				if (k == 1) dimVal = (3 * t * t * t - 6 * t * t + 4) / 6;
+				if (k == 2) dimVal = (-3 * t * t * t + 3 * t * t + 3 * t + 1) / 6;
+				if (k == 3) dimVal = t * t * t / 6;
+			}
+		}
+		value *= dimVal;
+	}
+	return value * b.weight;
+}
+
+// LCSample::getDerivInterpolationWeight (LCSample.cpp:92-105)
+double derivInterpolationWeight(const Function *f, const Sample &s, const double *pos, int direction)
+{
+	double combination = 0;
+	for (const Basis &b : s.basis)
+		combination += f->basisType == LOCO_CUBIC_BSPLINE ? evalDerivCubic(b, pos, direction, f->N) : evalDerivLinear(b, pos, direction, f->N);
+	return combination;
+}
+
 // LCAdaptiveGridCell::getAllInfluencingSamples (:558-607) with getNeightbourShapeInfoMappingMapping (:507-556;
 // only its failure mode matters: the value map is the identity, LCRealFunctionValueMap.cpp:13-25)
 int allInfluencingSamples(const Function *f, const Cell *cell, std::vector<std::pair<int, const std::vector<double> *>> *infl)
@@ -247,6 +305,26 @@ int cellEval(const Function *f, const Cell *cell, const double *pos, double *res
 		for (int j = 0; j < f->D; j++) { result[j] += w * (*s.second)[j]; vmax = std::max(vmax, std::fabs((*s.second)[j])); }
 		sc += std::fabs(w) * vmax;
 	}
+	if (scale) *scale = sc;
+	return LOCO_ST_OK;
+}
+
+// LCAdaptiveGridCell::evalDeriv (:678-711) + LCFunctionDeriv::newFromWeightedSum (LCFunctionDeriv.cpp:12-35)
+// + LCRealFunctionDeriv::add (LCRealFunctionDeriv.cpp:11-21); scalar functions only, like the reference
+int cellEvalDeriv(const Function *f, const Cell *cell, const double *pos, int direction, double *result, double *scale)
+{
+	if (!paramsInCell(cell, pos)) return LOCO_ST_OUTSIDE_CELL;
+	std::vector<std::pair<int, const std::vector<double> *>> infl;
+	int st = allInfluencingSamples(f, cell, &infl);
+	if (st != LOCO_ST_OK) return st;
+	if (infl.empty()) return LOCO_ST_EMPTY_SUPPORT;
+	double r = 0, sc = 0;
+	for (auto &s : infl) {
+		double w = derivInterpolationWeight(f, f->samples[s.first], pos, direction);
+		r += w * (*s.second)[0];
+		sc += std::fabs(w * (*s.second)[0]);
+	}
+	*result = r;
 	if (scale) *scale = sc;
 	return LOCO_ST_OK;
 }
@@ -359,6 +437,22 @@ void oracle_eval(void *h, const double *q, int64_t Q, double *out, int32_t *leaf
 	}
 }
 
+// LCSampledFunction::evalDeriv (LCSampledFunction.cpp:61-67) for each query, along cube direction `direction`
+void oracle_eval_deriv(void *h, const double *q, int64_t Q, int direction, double *out, int32_t *leaf, uint8_t *status, double *scale)
+{
+	Function *f = (Function *)h;
+	std::vector<double> p(f->N);
+	for (int64_t i = 0; i < Q; i++) {
+		mapToStandardHypercube(f, q + i * f->N, p.data());
+		Cell *cell = nullptr;
+		bool inside = getContainingLeaf(f->root, p.data(), &cell);
+		int st = inside ? cellEvalDeriv(f, cell, p.data(), direction, out + i, scale ? scale + i : nullptr) : LOCO_ST_OUTSIDE_CELL;
+		if (st != LOCO_ST_OK) { out[i] = NAN; if (scale) scale[i] = 0; }
+		if (leaf) leaf[i] = cell->leafIndex;
+		if (status) status[i] = (uint8_t)st;
+	}
+}
+
 // sorted sample indices of getAllInfluencingSamples; returns K, -1 if cap too small, -2 on LCError
 int oracle_support(void *h, int leafIdx, int32_t *ids, int cap)
 {
@@ -398,7 +492,7 @@ void oracle_error_check(void *h, const double *q, const double *truth, int64_t P
 		for (int j = 0; j < f->D; j++) {
 			double d = std::fabs(out[j] - truth[i * f->D + j]);
 			if (!((d - threshold) <= 0)) split[leaf] = 1;
-			if (!(d <= errMax[leaf])) errMax[leaf] = d;
+			if (!(d <= errMax[leaf]) && !std::isnan(errMax[leaf])) errMax[leaf] = d;  // a NaN error sticks (it forces the split)
 		}
 	}
 	if (nBad) *nBad = bad;
@@ -418,7 +512,7 @@ int oracle_center_error(void *h, double threshold, double *errMax, uint8_t *spli
 		for (int j = 0; j < f->D; j++) {
 			double d = std::fabs(out[j] - c->centerValue[j]);
 			if (!((d - threshold) <= 0)) split[l] = 1;
-			if (!(d <= errMax[l])) errMax[l] = d;
+			if (!(d <= errMax[l]) && !std::isnan(errMax[l])) errMax[l] = d;
 		}
 	}
 	return 0;

@@ -35,6 +35,7 @@ def lib():
         L.oracle_free.argtypes = [vp]
         L.oracle_num_leaves.argtypes = [vp]
         L.oracle_eval.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+        L.oracle_eval_deriv.argtypes = [vp, vp, i64, C.c_int, vp, vp, vp, vp]
         L.oracle_support.argtypes = [vp, C.c_int, vp, C.c_int]
         L.oracle_neighbors.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oracle_error_check.argtypes = [vp, vp, vp, i64, C.c_double, vp, vp, C.POINTER(i64)]
@@ -73,6 +74,14 @@ class Oracle:
         status = np.empty(Q, dtype=np.uint8); scale = np.empty(Q)
         lib().oracle_eval(self.h, _p(q), Q, _p(out), _p(leaf), _p(status), _p(scale))
         return (out[:, 0] if self.D == 1 else out), leaf, status, scale
+
+    def eval_deriv(self, q, direction):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)
+        Q = len(q)
+        out = np.empty(Q); leaf = np.empty(Q, dtype=np.int32)
+        status = np.empty(Q, dtype=np.uint8); scale = np.empty(Q)
+        lib().oracle_eval_deriv(self.h, _p(q), Q, direction, _p(out), _p(leaf), _p(status), _p(scale))
+        return out, leaf, status, scale
 
     def support(self, leaf, cap=1 << 20):
         ids = np.empty(cap, dtype=np.int32)

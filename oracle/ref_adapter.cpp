@@ -31,6 +31,8 @@
 #include "LCFunctionValue.h"
 #include "LCRealFunction.h"
 #include "LCRealFunctionValue.h"
+#include "LCFunctionDeriv.h"
+#include "LCRealFunctionDeriv.h"
 #include "LCAdaptiveSamplingParams.h"
 #include "LCBasisFunction.h"
 #include "LCSample.h"
@@ -433,6 +435,24 @@ void ref_fn_eval(void *fp, const double *q, long Q, double *out, int *leaf, unsi
 		LCError err = r->fn->evalShapeInfo(p, &v);
 		if (err.isOK()) { out[i] = realVal(v); delete v; }
 		else out[i] = NAN;
+	}
+}
+
+// LCSampledFunction::evalDeriv (LCSampledFunction.cpp:61-67) along cube direction `direction`.
+// out [Q] (NaN where the reference returned an error)
+void ref_fn_eval_deriv(void *fp, const double *q, long Q, int direction, double *out)
+{
+	CoutMute mute;
+	RefFn *r = (RefFn *)fp;
+	int N = r->fn->getNParams();
+	std::vector<double> p(N);
+	for (long i = 0; i < Q; i++) {
+		for (int d = 0; d < N; d++) p[d] = q[i * N + d];
+		LCFunctionDeriv *v = nullptr;
+		LCError err = r->fn->evalDeriv(p, direction, &v);
+		LCRealFunctionDeriv *rv = err.isOK() ? dynamic_cast<LCRealFunctionDeriv *>(v) : nullptr;
+		out[i] = rv ? rv->val : NAN;
+		delete rv;
 	}
 }
 

@@ -49,6 +49,7 @@ def lib():
         L.ref_fn_dump_cells.argtypes = [vp] * 9
         L.ref_fn_dump_border.argtypes = [vp] * 6
         L.ref_fn_eval.argtypes = [vp, vp, l, vp, vp, vp]
+        L.ref_fn_eval_deriv.argtypes = [vp, vp, l, i, vp]
         L.ref_fn_eval_sum.restype = d
         L.ref_fn_eval_sum.argtypes = [vp, vp, l]
         L.ref_fn_eval_fork.argtypes = [vp, vp, l, i]
@@ -158,6 +159,13 @@ class RefFn:
         lib().ref_fn_eval(self.h, _p(q), Q, _p(out), _p(leaf) if want_leaf else None,
                           _p(status) if want_leaf else None)
         return out, leaf, status
+
+    def eval_deriv(self, q, direction):
+        """LCSampledFunction::evalDeriv along cube direction `direction` (NaN where the reference returned an error)."""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)
+        out = np.empty(len(q))
+        lib().ref_fn_eval_deriv(self.h, _p(q), len(q), direction, _p(out))
+        return out
 
     def eval_sum(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)

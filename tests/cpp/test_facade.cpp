@@ -1,0 +1,268 @@
+// tests/cpp/test_facade.cpp -- the reference's own test scenarios (TestExamples/TestExamples.cpp) replayed against
+// the C++ facade (include/loco_lc.hpp) that stands in for the reference's class surface on the GPU path.
+//
+//   protoTest                        TestExamples.cpp:214-310   load a proto, 11x11 sweep, write, reload, sweep again, compare
+//   linearPrecisionTestLinear/Cubic  TestExamples.cpp:313-448   the interpolant of f = 1 + sum (i+1) x_i reproduces it (bound 1e-5 there)
+//   testFunctionLinearApproximation  TestExamples.cpp:185-211   sine-sum f, grid params (3,0.1,2,0) / (3,0.5,1,0), 21x21 sweep
+//   decideSplit                      LCAdaptiveGrid.cpp:578-626 CENTER_BASED and RANDOM_SAMPLES, batched over all leaves
+//   LCError behaviour                LCAdaptiveGridCell.cpp:438-454
+//
+// usage:  test_facade <golden .pb> <dump file> [--host-only]
+// Unlike the reference's mains (which print and always exit 0) every check counts: exit status = failed checks.
+// The sweep values are also written to <dump file> so that tests/test_facade.py can compare them with the oracle.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "loco_lc.hpp"
+
+static int g_failed = 0;
+#define CHECK(cond, what)                                                        \
+	do {                                                                         \
+		if (cond) std::printf("  verified: %s\n", what);                         \
+		else { std::printf("  NOT verified: %s\n", what); g_failed++; }          \
+	} while (0)
+
+// f = 1 + sum_i (i+1) x_i                       (LCRealFunction.cpp:64-71, linear variant)
+class LinearTestFunction : public LCFunction {
+public:
+	explicit LinearTestFunction(int n) : n_(n) {}
+	int getNParams() const override { return n_; }
+	double getMinRange(int) const override { return 0.0; }
+	double getMaxRange(int) const override { return 1.0; }
+	LCError evalShapeInfo(const std::vector<double> &p, LCFunctionValue **result) override
+	{
+		double v = 1;
+		for (int i = 0; i < n_; i++) v += (i + 1) * p[i];
+		*result = new LCRealFunctionValue(v);
+		return LCError();
+	}
+private:
+	int n_;
+};
+
+// f = 1 + sum_i sum_j a_ij sin(3 j x_i + p_ij)   (LCRealFunction.cpp:50-63 with fixed coefficients)
+class SineTestFunction : public LCFunction {
+public:
+	explicit SineTestFunction(int n) : n_(n) {}
+	int getNParams() const override { return n_; }
+	double getMinRange(int) const override { return 0.0; }
+	double getMaxRange(int) const override { return 1.0; }
+	double value(const std::vector<double> &p) const
+	{
+		double v = 1;
+		for (int i = 0; i < n_; i++)
+			for (int j = 0; j < 10; j++) v += (0.05 + 0.01 * ((7 * i + 3 * j) % 11)) * std::sin(3 * j * p[i] + 0.1 * (i + j));
+		return v;
+	}
+	LCError evalShapeInfo(const std::vector<double> &p, LCFunctionValue **result) override
+	{
+		*result = new LCRealFunctionValue(value(p));
+		return LCError();
+	}
+private:
+	int n_;
+};
+
+// a 3-component "mesh": (f, 2f, f*f)
+class VectorTestFunction : public SineTestFunction {
+public:
+	explicit VectorTestFunction(int n) : SineTestFunction(n) {}
+	LCError evalShapeInfo(const std::vector<double> &p, LCFunctionValue **result) override
+	{
+		const double v = value(p);
+		*result = new LCVectorFunctionValue(std::vector<double>{v, 2 * v, v * v});
+		return LCError();
+	}
+};
+
+// outputMatrix (TestExamples.cpp:108-142): n x n sweep over the first two parameters
+static LCError sweep2d(LCFunction *f, int n, std::vector<double> *vals)
+{
+	vals->clear();
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < n; j++) {
+			std::vector<double> p = {f->getMinRange(0) + (f->getMaxRange(0) - f->getMinRange(0)) * i / (n - 1.0),
+			                         f->getMinRange(1) + (f->getMaxRange(1) - f->getMinRange(1)) * j / (n - 1.0)};
+			LCFunctionValue *v = nullptr;
+			LCErrorReturn(f->evalShapeInfo(p, &v));
+			vals->push_back(v->data()[0]);
+			delete v;
+		}
+	return LCError();
+}
+
+static void protoTest(const std::string &pb, const std::string &dump, bool hostOnly)
+{
+	std::printf("protoTest (%s)\n", pb.c_str());
+	LCSampledFunction *shape = nullptr;
+	LCError err = PrecomputedParametricShapeConverter::loadFromProto(pb, false, &shape, hostOnly ? LOCO_HOST_ONLY : 0);
+	CHECK(err.isOK(), "loadFromProto");
+	if (!err.isOK()) { std::printf("    %s\n", err.internalDescription().c_str()); return; }
+	const std::string tmp = dump + ".roundtrip.pb";
+	CHECK(PrecomputedParametricShapeConverter::outputToProto(tmp, false, shape).isOK(), "outputToProto (binary)");
+	LCSampledFunction *again = nullptr;
+	CHECK(PrecomputedParametricShapeConverter::loadFromProto(tmp, false, &again, hostOnly ? LOCO_HOST_ONLY : 0).isOK(), "reload of the written proto");
+	CHECK(PrecomputedParametricShapeConverter::outputToProto(tmp + ".txt", true, shape).isOK(), "outputToProto (ascii)");
+	LCSampledFunction *fromText = nullptr;
+	CHECK(PrecomputedParametricShapeConverter::loadFromProto(tmp + ".txt", true, &fromText, hostOnly ? LOCO_HOST_ONLY : 0).isOK(), "reload of the ascii proto");
+	if (again && fromText) {
+		bool same = again->getNLeaves() == shape->getNLeaves() && again->getNSamples() == shape->getNSamples() && again->getNBorderCells() == shape->getNBorderCells() &&
+		            fromText->getNLeaves() == shape->getNLeaves() && fromText->getNSamples() == shape->getNSamples();
+		for (int l = 0; same && l < shape->getNLeaves(); l++) {
+			std::vector<int32_t> a, b, c;
+			shape->getInfluencingSampleIds(l, &a); again->getInfluencingSampleIds(l, &b); fromText->getInfluencingSampleIds(l, &c);
+			same = a == b && a == c;
+		}
+		CHECK(same, "leaf, sample and border counts and every influencing-sample set survive the round trip");
+	}
+	if (hostOnly) {
+		LCFunctionValue *v = nullptr;
+		LCError e = shape->evalShapeInfo(std::vector<double>(shape->getNParams(), 0.5), &v);
+		CHECK(!e.isOK() && e.internalDescription().find("no CPU path") != std::string::npos, "evaluation on a host-only model fails loudly (no CPU path)");
+	} else if (again) {
+		std::vector<double> a, b;
+		CHECK(sweep2d(shape, 11, &a).isOK() && sweep2d(again, 11, &b).isOK(), "11x11 evaluation sweeps");
+		CHECK(a == b, "sweep of the reloaded function is identical");
+		// the same sweep through the batch entry point
+		std::vector<double> q, out(a.size());
+		for (int i = 0; i < 11; i++) for (int j = 0; j < 11; j++) { q.push_back(i / 10.0 * (shape->getMaxRange(0) - shape->getMinRange(0)) + shape->getMinRange(0)); q.push_back(j / 10.0 * (shape->getMaxRange(1) - shape->getMinRange(1)) + shape->getMinRange(1)); }
+		std::vector<uint8_t> st(a.size());
+		CHECK(shape->evalShapeInfoBatch(q.data(), (int64_t)a.size(), out.data(), nullptr, st.data()).isOK(), "evalShapeInfoBatch");
+		CHECK(out == a, "batch of 121 == 121 batches of one");
+		FILE *fp = std::fopen(dump.c_str(), "w");
+		if (fp) {
+			for (size_t i = 0; i < a.size(); i++) std::fprintf(fp, "%.17g %.17g %.17g\n", q[2 * i], q[2 * i + 1], a[i]);
+			std::fclose(fp);
+		}
+		// LCError behaviour
+		LCFunctionValue *v = nullptr;
+		LCError e1 = shape->evalShapeInfo(std::vector<double>{shape->getMaxRange(0) + 0.5, shape->getMinRange(1)}, &v);
+		CHECK(!e1.isOK() && e1.internalDescription() == "parameter ouside cell", "query outside the domain -> \"parameter ouside cell\"");
+		LCError e2 = shape->evalShapeInfo(std::vector<double>{0.5}, &v);
+		CHECK(!e2.isOK() && e2.internalDescription() == "invalid number of parameters", "wrong arity -> \"invalid number of parameters\"");
+	}
+	delete shape; delete again; delete fromText;
+}
+
+static void linearPrecisionTest(int N, LCBasisFunction::LCBasisFunctionType basis, int boot)
+{
+	std::printf("linearPrecisionTest N=%d %s bootstrap %d\n", N, basis == LCBasisFunction::CUBIC_BSPLINE ? "cubic" : "linear", boot);
+	LinearTestFunction f(N);
+	LCAdaptiveSamplingParams params(0, 0.1, boot, 0);
+	LCAdaptiveGrid grid(&f, basis, &params, true);
+	CHECK(grid.status().isOK(), "grid construction");
+	if (!grid.status().isOK()) return;
+	std::vector<double> ranges;
+	f.getRanges(&ranges);
+	// the reference's call pattern (TestExamples.cpp:196-199)
+	LCSampledFunction *approx = new LCSampledFunction(grid.getRoot(), ranges, grid.getSamples(), grid.getBorderCells());
+	approx->addBorderCells();
+	int n = 11;
+	long total = 1;
+	for (int i = 0; i < N; i++) total *= n;
+	double worst = 0, worstDeriv = 0;
+	bool ok = true;
+	for (long e = 0; e < total; e++) {
+		std::vector<double> p(N);
+		long r = e;
+		for (int i = 0; i < N; i++) { p[i] = (r % n) / (n - 1.0); r /= n; }
+		LCFunctionValue *a = nullptr, *b = nullptr;
+		ok = ok && approx->evalShapeInfo(p, &a).isOK() && f.evalShapeInfo(p, &b).isOK();
+		if (!ok) break;
+		double diff;
+		a->computeDifference(b, &diff);
+		worst = std::max(worst, diff);
+		delete a; delete b;
+		bool interior = true;
+		for (int i = 0; i < N; i++) interior = interior && p[i] > 0 && p[i] < 1;
+		if (basis == LCBasisFunction::CUBIC_BSPLINE && interior)
+			for (int d = 0; d < N; d++) {
+				LCFunctionDeriv *dv = nullptr;
+				ok = ok && approx->evalDeriv(p, d, &dv).isOK();
+				if (!ok) break;
+				worstDeriv = std::max(worstDeriv, std::fabs(static_cast<LCRealFunctionDeriv *>(dv)->val - (d + 1) / 2.0));
+				delete dv;
+			}
+	}
+	CHECK(ok, "all evaluations returned LCError OK");
+	std::printf("    max |approx - exact| = %.3e, max derivative error = %.3e\n", worst, worstDeriv);
+	CHECK(worst <= 1e-5, "linear precision within the reference's bound 1e-5");
+	CHECK(worst <= 1e-12, "linear precision within 1e-12");
+	CHECK(worstDeriv <= 1e-11, "cubic evalDeriv of a linear function is its slope (cube coordinates)");
+	delete approx;
+}
+
+static void functionApproximationTest(double thr, int maxDepth, int boot)
+{
+	std::printf("testFunctionLinearApproximation (%g, %d, %d) cubic\n", thr, maxDepth, boot);
+	SineTestFunction f(2);
+	LCAdaptiveSamplingParams params(maxDepth, thr, boot, 0);
+	LCAdaptiveGrid grid(&f, LCBasisFunction::CUBIC_BSPLINE, &params, true);
+	CHECK(grid.status().isOK(), "grid construction");
+	if (!grid.status().isOK()) return;
+	std::vector<double> exact, approx;
+	CHECK(sweep2d(&f, 21, &exact).isOK() && sweep2d(grid.getSampledFunction(), 21, &approx).isOK(), "21x21 sweeps of the function and of its interpolant");
+	double worst = 0;
+	bool finite = true;
+	for (size_t i = 0; i < exact.size(); i++) { worst = std::max(worst, std::fabs(exact[i] - approx[i])); finite = finite && std::isfinite(approx[i]); }
+	std::printf("    max |approx - exact| over the sweep = %.4f\n", worst);
+	CHECK(finite && worst < 1.0, "interpolant is finite and tracks the function");
+	// decideSplit for every leaf in one batch
+	std::vector<uint8_t> split;
+	std::vector<double> err;
+	CHECK(grid.decideSplitBatch(&split, &err).isOK(), "decideSplitBatch CENTER_BASED");
+	bool consistent = (int64_t)split.size() == grid.getSampledFunction()->getNLeaves();
+	const bool mayRefine = 2 * boot < maxDepth;
+	for (size_t l = 0; consistent && l < split.size(); l++) consistent = split[l] == (mayRefine && !((err[l] - thr) <= 0) ? 1 : 0);
+	CHECK(consistent, "split[l] == (level < maxTreeDepth && !(err - threshold <= 0))");
+	LCAdaptiveSamplingParams rnd(maxDepth + 4, thr, boot, 8, LCAdaptiveSamplingParams::ERROR_BASED, LCAdaptiveSamplingParams::RANDOM_SAMPLES);
+	LCAdaptiveGrid grid2(&f, LCBasisFunction::CUBIC_BSPLINE, &rnd, true);
+	std::vector<uint8_t> split2;
+	std::vector<double> err2;
+	srand(7);
+	CHECK(grid2.decideSplitBatch(&split2, &err2).isOK(), "decideSplitBatch RANDOM_SAMPLES (8 jitter points per leaf)");
+	bool c2 = split2.size() == split.size();
+	for (size_t l = 0; c2 && l < split2.size(); l++) c2 = split2[l] == (!((err2[l] - thr) <= 0) ? 1 : 0) && std::isfinite(err2[l]);
+	CHECK(c2, "RANDOM_SAMPLES flags follow the per-leaf maximum error");
+}
+
+static void vectorValuedTest()
+{
+	std::printf("vector-valued function (3 components per sample)\n");
+	VectorTestFunction f(2);
+	SineTestFunction f0(2);
+	LCAdaptiveSamplingParams params(0, 0.1, 2, 0);
+	LCAdaptiveGrid grid(&f, LCBasisFunction::CUBIC_BSPLINE, &params, true), grid0(&f0, LCBasisFunction::CUBIC_BSPLINE, &params, true);
+	CHECK(grid.status().isOK() && grid0.status().isOK(), "grid construction");
+	if (!grid.status().isOK() || !grid0.status().isOK()) return;
+	bool ok = true;
+	double worst = 0;
+	for (int i = 0; i <= 10 && ok; i++) {
+		std::vector<double> p = {i / 10.0, 0.37};
+		LCFunctionValue *v = nullptr, *s = nullptr;
+		ok = grid.evalShapeInfo(p, &v).isOK() && grid0.evalShapeInfo(p, &s).isOK() && v->size() == 3;
+		if (ok) worst = std::max(worst, std::max(std::fabs(v->data()[0] - s->data()[0]), std::fabs(v->data()[1] - 2 * s->data()[0])));
+		delete v; delete s;
+	}
+	CHECK(ok && worst < 1e-13, "components 0 and 1 equal the scalar interpolant of f and 2f (linearity of the weighted sum)");
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 3) { std::printf("usage: %s <golden .pb> <dump file> [--host-only]\n", argv[0]); return 2; }
+	const bool hostOnly = argc > 3 && !std::strcmp(argv[3], "--host-only");
+	protoTest(argv[1], argv[2], hostOnly);
+	if (!hostOnly) {
+		linearPrecisionTest(1, LCBasisFunction::CUBIC_BSPLINE, 2);
+		linearPrecisionTest(3, LCBasisFunction::CUBIC_BSPLINE, 1);
+		linearPrecisionTest(2, LCBasisFunction::LINEAR_BSPLINE, 2);
+		functionApproximationTest(0.1, 3, 2);
+		functionApproximationTest(0.5, 3, 1);
+		vectorValuedTest();
+	}
+	std::printf("%s: %d check(s) failed\n", g_failed ? "FAILED" : "PASSED", g_failed);
+	return g_failed;
+}

@@ -172,3 +172,22 @@ def test_mesh_ring_checksum():
     v = m.get_values(5, 2)
     j = np.arange(D)
     assert np.allclose(v[0], np.sin(0.37 * j + 0.61 * 5 + 0.25) + 0.001 * (j % 97), atol=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_derivative_golden_vectors(golden, name):
+    """LCSampledFunction::evalDeriv batch vs the reference's own output and vs the restatement."""
+    pb, z = golden(name)
+    ref = np.load(pb[:-3] + ".deriv.npz")["deriv"]
+    m = capi.Model.from_proto(pb, device=0)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    for d in range(m.N):
+        out, leaf, status = m.eval_deriv(z["q"], d)
+        o_out, o_leaf, o_status, scale = orc.eval_deriv(z["q"], d)
+        assert np.array_equal(leaf, z["leaf"]) and np.array_equal(status, z["status"])
+        ok = status == 0
+        assert_values_close(out[ok], ref[d][ok], scale[ok])
+        assert_values_close(out[ok], o_out[ok], scale[ok])
+        assert np.isnan(out[~ok]).all()
+    with pytest.raises(capi.LocoError):
+        m.eval_deriv(z["q"], m.N)

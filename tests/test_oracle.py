@@ -108,3 +108,31 @@ def test_mesh_valued_restatement_matches_scalar_reference():
         ids, w = fn.weights(int(leaf[i]), q[i] * 2 - 1)
         ref = (w[:, None] * table[ids]).sum(axis=0)
         assert np.abs(out[i] - ref).max() <= 1e-12 * max(scale[i], 1e-300)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_derivative_matches_golden(golden, name):
+    """LCSampledFunction::evalDeriv (LCSampledFunction.cpp:61-67): restatement vs the reference's own output
+    (tests/golden/make_golden_deriv.py), every cube direction.  The linear basis is restated literally,
+    including the reference's signed-distance test (LCBasisFunction.cpp:295-332)."""
+    import os
+    pb, z = golden(name)
+    ref = np.load(pb[:-3] + ".deriv.npz")["deriv"]
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    for d in range(orc.N):
+        out, leaf, status, scale = orc.eval_deriv(z["q"], d)
+        assert np.array_equal(leaf, z["leaf"]) and np.array_equal(status, z["status"])
+        ok = status == 0
+        assert_values_close(out[ok], ref[d][ok], scale[ok])
+        assert np.isnan(out[~ok]).all() and np.isnan(ref[d][~ok]).all()
+
+
+@pytest.mark.parametrize("name", ["cub2d_prototest", "cub1d_linprec"])
+def test_cubic_derivative_of_linear_function(golden, name):
+    """known answer: the cubic interpolant reproduces f = 1 + sum (i+1) x_i, so d/d(cube_i) = (i+1)/2 on [0,1]^N"""
+    pb, z = golden(name)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    inside = (z["q"] > 0).all(axis=1) & (z["q"] < 1).all(axis=1)
+    for d in range(orc.N):
+        out, _, status, _ = orc.eval_deriv(z["q"], d)
+        assert np.abs(out[inside & (status == 0)] - (d + 1) / 2).max() < 1e-11
