@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted tiles")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted TMA tiles, 4 L2-resident sorted chunks")
+    ap.add_argument("--chunk", type=int, default=0, help="queries per L2-resident chunk of the sorted path (0 = auto)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.queries:
@@ -217,6 +218,7 @@ def main():
         dist.barrier()
     m, amp, phase = build_model(capi, w, local)
     m.set_option("path", args.path)
+    m.set_option("chunk", args.chunk)
     info = m.info
     N, D, Q = w["N"], w["D"], w["Q"]
     gen = torch.Generator("cuda").manual_seed(1234 + rank)

@@ -210,7 +210,9 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
                                       uint8_t *split, void *cuda_stream);
 
 /* ---- tuning / accounting -------------------------------------------------------------------------------- */
-/* options: "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted tiles | 3 direct without the tensor-leaf shortcut;  "fp32" 0|1 (scalar weights in fp32) */
+/* options: "lut" 1 locate grid before the k-d descent (default) | 0 descent from the root only;
+ *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
+ *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto) */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);

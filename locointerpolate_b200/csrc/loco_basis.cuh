@@ -36,9 +36,9 @@ __device__ __forceinline__ void map_to_cube(const DeviceModel &m, const double *
 	const int N = NT > 0 ? NT : m.N;
 #pragma unroll
 	for (int d = 0; d < N; d++) {
-		const double mn = m.dom_min[d], mx = m.dom_max[d];
-		const double alpha = __ddiv_rn(__dsub_rn(p[d], mn), __dsub_rn(mx, mn));
-		x.set(d, __dsub_rn(__dmul_rn(alpha, 2.0), 1.0));
+		const double num = __dsub_rn(p[d], m.dom_lo[d]);
+		const double alpha = ((m.dom_exact_mask >> d) & 1u) ? __dmul_rn(num, m.dom_rcp[d]) : __ddiv_rn(num, m.dom_w[d]);
+		x.set(d, __fma_rn(alpha, 2.0, -1.0));  // alpha*2 is exact, so the fused form rounds exactly like alpha*2 - 1
 	}
 }
 
@@ -49,6 +49,33 @@ __device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT>
 {
 	if (m.n_inner == 0) return 0;  // the root is a leaf
 	uint32_t c = 0;
+	if (m.lut) {
+		// locate grid: the grid cell is found with EXACT comparisons against the stored boundaries (the
+		// multiplication only proposes a candidate), its entry names the deepest tree cell containing the whole
+		// grid cell, and the descent resumes there.  Any inconsistency (NaN, estimate off by more than one
+		// cell) falls back to the descent from the root, so the result is always the reference's leaf.
+		const int N = NT > 0 ? NT : m.N;
+		uint32_t idx = 0;
+		int shift = 0;
+		bool ok = true;
+#pragma unroll
+		for (int d = 0; d < N; d++) {
+			const int bits = m.lut_bits[d];
+			if (bits == 0) continue;
+			const int last = (1 << bits) - 1;
+			const double *B = m.lut_bounds + m.lut_boff[d];
+			const double xv = x.get(d);
+			int i = (int)fmin(fmax((xv - m.lut_lo[d]) * m.lut_inv[d], 0.0), (double)last);
+			double b0 = __ldg(B + i), b1 = __ldg(B + i + 1);
+			if (i > 0 && xv < b0) { i--; b1 = b0; b0 = __ldg(B + i); }              // rare: the estimate rounded across a boundary
+			else if (i < last && !(xv < b1)) { i++; b0 = b1; b1 = __ldg(B + i + 1); }
+			ok &= (i == 0 || !(xv < b0)) && (i == last || xv < b1);
+			idx |= (uint32_t)i << shift;
+			shift += bits;
+		}
+		if (ok) c = __ldg(m.lut + idx);
+		if (c & kLeafFlag) return (int32_t)(c & (kLeafFlag - 1));
+	}
 	for (;;) {
 		const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.cells + c));
 		const double split = __hiloint2double((int)raw.y, (int)raw.x);
@@ -158,6 +185,29 @@ struct TensorContract<NT, F, 0> {
 			const double2 p = *reinterpret_cast<const double2 *>(v + j);
 			s += f[0][j] * p.x;
 			s += f[0][j + 1] * p.y;
+		}
+		return s;
+	}
+};
+// level 1: one F x F slab.  All of its values are requested FIRST (F*F/2 independent 128-bit loads in flight
+// together), then contracted from registers: one exposed load latency per slab instead of one per row.
+template <int NT, int F>
+struct TensorContract<NT, F, 1> {
+	static __device__ __forceinline__ double run(const double *v, const double (&f)[NT][F], int)
+	{
+		double2 t[F * F / 2];
+#pragma unroll
+		for (int i = 0; i < F * F / 2; i++) t[i] = reinterpret_cast<const double2 *>(v)[i];
+		double s = 0.0;
+#pragma unroll
+		for (int j = 0; j < F; j++) {
+			double s0 = 0.0;
+#pragma unroll
+			for (int i = 0; i < F / 2; i++) {
+				s0 += f[0][2 * i] * t[j * (F / 2) + i].x;
+				s0 += f[0][2 * i + 1] * t[j * (F / 2) + i].y;
+			}
+			s += f[1][j] * s0;
 		}
 		return s;
 	}

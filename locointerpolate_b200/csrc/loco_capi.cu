@@ -27,8 +27,8 @@ const int kSlots = 3;  // pipeline depth of the host-buffer path
 
 struct Workspace {
 	cudaStream_t stream = nullptr;
-	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr;
-	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0;
+	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr, *sorted = nullptr;
+	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0, sorted_b = 0;
 };
 
 } // namespace
@@ -48,7 +48,8 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0;
+	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 };
 
@@ -196,6 +197,28 @@ int build_device_model(loco_model *m)
 		dm.tl_block = dblk;
 		if ((rc = upload(m, f.tl_row, &dm.tl_row))) return rc;
 	}
+	dm.dom_exact_mask = 0;
+	for (int d = 0; d < f.N; d++) {
+		dm.dom_lo[d] = f.dom_min[(size_t)d];
+		dm.dom_w[d] = f.dom_max[(size_t)d] - f.dom_min[(size_t)d];  // LCFunction.cpp:66: getMaxRange(i) - getMinRange(i)
+		int e;
+		const bool pow2 = dm.dom_w[d] > 0 && std::isfinite(dm.dom_w[d]) && std::frexp(dm.dom_w[d], &e) == 0.5 && std::isnormal(dm.dom_w[d]) &&
+		                  std::isnormal(1.0 / dm.dom_w[d]);
+		dm.dom_rcp[d] = pow2 ? 1.0 / dm.dom_w[d] : 0.0;
+		if (pow2) dm.dom_exact_mask |= 1u << d;
+	}
+	dm.lut = nullptr;
+	if (!f.lut.empty() && m->opt_lut) {
+		if ((rc = upload(m, f.lut, &dm.lut))) return rc;
+		if ((rc = upload(m, f.lut_bounds, &dm.lut_bounds))) return rc;
+		for (int d = 0; d < f.N; d++) {
+			dm.lut_bits[d] = f.lut_bits[d];
+			dm.lut_boff[d] = f.lut_boff[d];
+			const double lo = f.lut_bounds[(size_t)f.lut_boff[d]], hi = f.lut_bounds[(size_t)f.lut_boff[d] + ((size_t)1 << f.lut_bits[d])];
+			dm.lut_lo[d] = lo;
+			dm.lut_inv[d] = (double)((int64_t)1 << f.lut_bits[d]) / (hi - lo);
+		}
+	}
 	dm.path_consistent = f.path_consistent ? 1 : 0;
 	dm.any_leaf_status = f.any_leaf_status ? 1 : 0;
 	for (int i = 0; i < f.N; i++) {
@@ -238,8 +261,24 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		// leaf-sorted tiles pay off once a leaf bucket fills a good part of a 256-query tile
 		// and the per-leaf data no longer sits in the L1 anyway
 		const int64_t leaf_bytes = dm.tensor_F > 0 ? (int64_t)dm.L * dm.tl_stride * 8 : m->n_terms * (16 * dm.N + 8);
-		const bool tiles = !in_cube && (m->opt_path == 2 || (m->opt_path == 0 && Q >= (int64_t)dm.L * 48 && leaf_bytes > 96 * 1024));
-		if (tiles) {
+		const bool big = Q >= (int64_t)dm.L * 24 && Q >= (1 << 16) && leaf_bytes > 96 * 1024;
+		const bool sorted = !in_cube && (m->opt_path == 4 || (m->opt_path == 0 && big));
+		const bool tiles = !in_cube && m->opt_path == 2;
+		if (sorted) {
+			// chunks sized so that records (32 B/query) + the out slice stay L2 resident; never fewer than ~16 queries per leaf
+			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 23, (int64_t)dm.L * 16);
+			chunk = std::min(chunk, Q);
+			int rc;
+			if ((rc = grow(m, &w.sorted, &w.sorted_b, sorted_work_bytes(dm, chunk)))) return rc;
+			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+			const SortedWork sw = carve_sorted_work(dm, w.sorted);
+			launch_sorted_reset(dm, sw, st);
+			for (int64_t o = 0; o < Q; o += chunk) {
+				const int64_t n = std::min(chunk, Q - o);
+				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw, m->sm_count, st);
+			}
+		} else if (tiles) {
 			int rc;
 			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
 			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
@@ -400,7 +439,7 @@ void loco_free(loco_model_t *m)
 	for (void *p : m->allocs) cudaFree(p);
 	for (int s = 0; s < kSlots; s++) {
 		Workspace &w = m->ws[s];
-		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc}) if (p) cudaFree(p);
+		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted}) if (p) cudaFree(p);
 		if (w.stream) cudaStreamDestroy(w.stream);
 	}
 	delete m;
@@ -722,6 +761,13 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!m || !name) return fail(m, LOCO_ERR_INVALID, "null argument");
 	if (!strcmp(name, "path")) { m->opt_path = value; return LOCO_OK; }
 	if (!strcmp(name, "fp32")) { m->opt_fp32 = value; return LOCO_OK; }
+	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
+	if (!strcmp(name, "lut")) {  // 0: plain k-d descent from the root, 1: locate grid first (default)
+		if (m->dm.lut) m->d_lut = m->dm.lut;
+		m->opt_lut = value;
+		m->dm.lut = value ? m->d_lut : nullptr;
+		return LOCO_OK;
+	}
 	return fail(m, LOCO_ERR_INVALID, std::string("unknown option ") + name);
 }
 

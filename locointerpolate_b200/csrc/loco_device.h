@@ -15,6 +15,10 @@ struct DeviceModel {
 	int32_t L, C, n_inner, max_support, max_terms;
 	int64_t R, value_stride;          // rows and row stride (doubles) of the value table
 	const double *dom_min, *dom_max;  // [N]
+	// the same in the kernel parameter bank: min, max-min (the reference's own subtraction) and, where max-min is a
+	// power of two, its exact reciprocal: (p-min)*(1/w) is then bit-identical to (p-min)/w
+	double dom_lo[kMaxN], dom_w[kMaxN], dom_rcp[kMaxN];
+	uint32_t dom_exact_mask;
 	const TreeCell *cells;            // [n_inner] inner cells of the k-d tree in pre-order, 16 B each
 	const double *leaf_lo_eps, *leaf_hi_eps;  // [L*N]
 	const double *leaf_lo, *leaf_hi;          // [L*N]
@@ -38,6 +42,11 @@ struct DeviceModel {
 	int32_t tensor_F, tensor_K, tl_stride, tl_voff;
 	const double *tl_block;           // [L * tl_stride]
 	const int32_t *tl_row;            // [L * F^N] value rows in tensor order
+	// locate grid (Flat::lut): lut == nullptr disables it
+	const uint32_t *lut;
+	const double *lut_bounds;
+	int32_t lut_bits[kMaxN], lut_boff[kMaxN];
+	double lut_lo[kMaxN], lut_inv[kMaxN];   // estimate of the grid cell: (x - lo) * inv, then exact comparisons
 	// containment against the root box only (valid when every leaf box is implied by its split planes)
 	int32_t path_consistent, any_leaf_status;
 	double root_lo_eps[kMaxN], root_hi_eps[kMaxN];
@@ -96,5 +105,18 @@ int launch_mesh_tensor_tiles(const DeviceModel &m, const SortWork &w, const uint
                              cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
+
+// ---- L2-resident sorted chunks (loco_sorted.cu)
+struct SortedWork {
+	int32_t *count;    // [L] histogram (zero between chunks)
+	int32_t *cursor;   // [L+1] bucket cursors; [L] = number of records of the chunk
+	unsigned *done;    // arrival counter of the count kernel
+	double *xs;        // [chunk * record] leaf-ordered query records
+};
+size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk);
+SortedWork carve_sorted_work(const DeviceModel &m, void *base);
+int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t st);
+int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
+                                    int sm_count, cudaStream_t st);
 
 } // namespace loco

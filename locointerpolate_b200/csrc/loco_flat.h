@@ -94,6 +94,18 @@ struct Flat {
 	bool path_consistent = false;
 	bool any_leaf_status = false;
 
+	// ---- locate grid ---------------------------------------------------------------------------------------
+	// A regular grid of prod_d 2^lut_bits[d] cells over the root box; entry = code (see TreeCell) of the DEEPEST
+	// tree cell whose region -- as defined by the split comparisons on its root path -- contains the whole grid
+	// cell.  A query finds its grid cell with exact comparisons against the stored boundaries and resumes the
+	// descent from that tree cell: on trees whose top levels are balanced (every bootstrap grid) the k-d descent
+	// of getCointainingLeaf collapses to one load.  Outer grid cells extend to +-infinity, NaN coordinates map
+	// to the last cell (the reference's `x < split` is false for NaN: always child2).
+	int32_t lut_bits[16] = {0};
+	std::vector<uint32_t> lut;         // [prod 2^bits], dimension 0 fastest; empty when the root is a leaf
+	std::vector<double> lut_bounds;    // per dimension 2^bits+1 boundaries, concatenated
+	int32_t lut_boff[16] = {0};        // offset of dimension d in lut_bounds
+
 	// leaf adjacency kept for introspection / tests
 	std::vector<int32_t> n_leaf_neighbors, n_border_neighbors;  // [L]
 };

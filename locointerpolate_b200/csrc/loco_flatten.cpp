@@ -361,6 +361,85 @@ Status flatten(const Graph &g, Flat *out)
 	}
 	for (uint8_t s : f.leaf_status) f.any_leaf_status |= s != ST_OK;
 
+	// ---- locate grid (see loco_flat.h) -------------------------------------------------------------------------
+	if (n_inner > 0) {
+		const int kMaxLutBits = 17;
+		// one bit per tree level, given to the dimension most cells of that level split
+		std::vector<std::vector<int64_t>> by_level;
+		for (int64_t c = 0; c < f.C; c++) {
+			if (g.tree.split_dir[c] < 0) continue;
+			if ((size_t)level[(size_t)c] >= by_level.size()) by_level.resize((size_t)level[(size_t)c] + 1, std::vector<int64_t>((size_t)N, 0));
+			by_level[(size_t)level[(size_t)c]][(size_t)g.tree.split_dir[c]]++;
+		}
+		int total_bits = 0;
+		for (size_t lv = 0; lv < by_level.size() && total_bits < kMaxLutBits; lv++) {
+			int best = (int)(std::max_element(by_level[lv].begin(), by_level[lv].end()) - by_level[lv].begin());
+			f.lut_bits[best]++;
+			total_bits++;
+		}
+		std::vector<int64_t> stride((size_t)N);
+		int64_t entries = 1;
+		for (int d = 0; d < N; d++) {
+			stride[(size_t)d] = entries;
+			entries <<= f.lut_bits[d];
+			f.lut_boff[d] = (int32_t)f.lut_bounds.size();
+			const int64_t G = (int64_t)1 << f.lut_bits[d];
+			const double lo = g.tree.ranges[2 * d], hi = g.tree.ranges[2 * d + 1];
+			for (int64_t i = 0; i <= G; i++) f.lut_bounds.push_back(i == G ? hi : lo + (hi - lo) * ((double)i / (double)G));
+		}
+		f.lut.assign((size_t)entries, 0u);
+		std::vector<int64_t> a((size_t)N, 0), b((size_t)N);
+		for (int d = 0; d < N; d++) b[(size_t)d] = (int64_t)1 << f.lut_bits[d];
+		// fill the (non-empty) index box [a, b) with `code`
+		auto fill = [&](const std::vector<int64_t> &lo_i, const std::vector<int64_t> &hi_i, uint32_t cd) {
+			std::vector<int64_t> it(lo_i);
+			for (;;) {
+				int64_t idx = 0;
+				for (int d = 0; d < N; d++) idx += it[(size_t)d] * stride[(size_t)d];
+				// dimension 0 is contiguous
+				for (int64_t i0 = lo_i[0]; i0 < hi_i[0]; i0++) f.lut[(size_t)(idx - it[0] + i0)] = cd;
+				int d = 1;
+				for (; d < N; d++) {
+					if (++it[(size_t)d] < hi_i[(size_t)d]) break;
+					it[(size_t)d] = lo_i[(size_t)d];
+				}
+				if (d >= N) break;
+			}
+		};
+		// recursive split of the index box along the tree (explicit stack: trees may be deep)
+		struct Item { int64_t cell; std::vector<int64_t> a, b; };
+		std::vector<Item> stack;
+		stack.push_back({0, a, b});
+		while (!stack.empty()) {
+			Item it = std::move(stack.back());
+			stack.pop_back();
+			bool empty = false;
+			for (int d = 0; d < N; d++) empty |= it.a[(size_t)d] >= it.b[(size_t)d];
+			if (empty) continue;
+			const int32_t dir = g.tree.split_dir[it.cell];
+			if (dir < 0) { fill(it.a, it.b, code(it.cell)); continue; }
+			const double sv = g.tree.split_val[it.cell];
+			const double *B = &f.lut_bounds[(size_t)f.lut_boff[dir]];
+			const int64_t G = (int64_t)1 << f.lut_bits[dir];
+			// grid cell i covers [B[i], B[i+1]) with B[0] = -inf and B[G] = +inf.
+			// child1 (x < sv) contains it iff upper(i) <= sv; child2 (x >= sv, or NaN) iff lower(i) >= sv.
+			int64_t j1 = it.a[(size_t)dir];
+			while (j1 < it.b[(size_t)dir] && j1 + 1 < G && B[j1 + 1] <= sv) j1++;   // cells [a, j1) lie in child1
+			int64_t j2 = j1;
+			while (j2 < it.b[(size_t)dir] && !(j2 > 0 && B[j2] >= sv)) j2++;          // cells [j2, b) lie in child2
+			if (j2 > j1) {  // straddling cells: the descent resumes at this tree cell
+				Item mid{it.cell, it.a, it.b};
+				mid.a[(size_t)dir] = j1; mid.b[(size_t)dir] = j2;
+				fill(mid.a, mid.b, code(it.cell));
+			}
+			Item left{it.cell + 1, it.a, it.b}, right{g.tree.child2[it.cell], it.a, it.b};
+			left.b[(size_t)dir] = j1;
+			right.a[(size_t)dir] = j2;
+			stack.push_back(std::move(left));
+			stack.push_back(std::move(right));
+		}
+	}
+
 	f.sample_row = g.sample_row;
 	f.values = g.values;
 	return Status();

@@ -20,7 +20,7 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("path", [1, 2, 3, 4])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_vectors(golden, name, path):
     pb, z = golden(name)
@@ -191,3 +191,49 @@ def test_derivative_golden_vectors(golden, name):
         assert np.isnan(out[~ok]).all()
     with pytest.raises(capi.LocoError):
         m.eval_deriv(z["q"], m.N)
+
+
+def _adversarial_queries(N, n, seed):
+    """uniform points plus points on / one ulp either side of dyadic planes (where split planes and grid boundaries lie)"""
+    rng = np.random.default_rng(seed)
+    q = rng.random((n, N)) * 1.00001 - 0.000005
+    k = n // 2
+    planes = rng.integers(0, 65, (k, N)) / 64.0
+    nudge = rng.integers(-1, 2, (k, N))
+    q[:k] = np.where(nudge == 0, planes, np.nextafter(planes, np.where(nudge > 0, 2.0, -1.0)))
+    q[k] = np.nan
+    q[k + 1, 0] = np.nan
+    q[k + 2, -1] = np.inf
+    q[k + 3, 0] = -np.inf
+    return q
+
+
+@pytest.mark.parametrize("name", ["cub2d_adapt6", "lin3d_adapt5", "lin2d_adapt6", "cub3d_boot2", "lin4d_boot1", "cub1d_linprec"])
+def test_locate_grid_equals_descent_golden(golden, name):
+    """The locate grid (Flat::lut) must name exactly the leaf the k-d descent from the root reaches."""
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    q = np.concatenate([z["q"], _adversarial_queries(m.N, 200_000, 3)])
+    for path in (1, 2, 4):
+        m.set_option("path", path)
+        m.set_option("chunk", 50_000)
+        m.set_option("lut", 0)
+        out0, leaf0, status0 = m.eval(q)
+        m.set_option("lut", 1)
+        out1, leaf1, status1 = m.eval(q)
+        assert np.array_equal(leaf0, leaf1) and np.array_equal(status0, status1)
+        assert np.array_equal(out0, out1, equal_nan=True)
+    assert np.array_equal(leaf1[:len(z["q"])], z["leaf"])
+
+
+@pytest.mark.parametrize("N,basis,level", [(3, capi.CUBIC, 5), (2, capi.LINEAR, 9), (6, capi.LINEAR, 2), (8, capi.LINEAR, 1)])
+def test_locate_grid_equals_descent_bootstrap(N, basis, level):
+    m = capi.Model.bootstrap(N, basis, level, 1, True, fn=lambda p: float(p.sum()), device=0)
+    q = _adversarial_queries(N, 1_000_000, 4)
+    m.set_option("path", 1)
+    m.set_option("lut", 0)
+    _, leaf0, status0 = m.eval(q)
+    m.set_option("lut", 1)
+    _, leaf1, status1 = m.eval(q)
+    assert np.array_equal(leaf0, leaf1) and np.array_equal(status0, status1)
+    assert leaf1.max() == m.L - 1
