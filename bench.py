@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (c3, c4) reported under other_workloads")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted TMA tiles, 4 L2-resident sorted chunks")
     ap.add_argument("--chunk", type=int, default=0, help="queries per L2-resident chunk of the sorted path (0 = auto)")
     args = ap.parse_args()
@@ -216,6 +217,48 @@ def main():
         product_build.build()
     if world > 1:
         dist.barrier()
+
+    line = measure(args.workload, w, args, rank, world, local, config, full=True)
+    # the other single-GPU configurations of BASELINE.json, measured the same way with fewer steps (secondary numbers;
+    # the headline stays the workload named in `config`)
+    if not args.no_extra and args.workload == "c2":
+        extra = {}
+        for name in ("c3", "c4"):
+            try:
+                torch.cuda.empty_cache()
+                wx = dict(WORKLOADS[name])
+                r = measure(name, wx, args, rank, world, local, None, full=False)
+                extra[name] = r
+            except Exception as e:  # a secondary number must never take the headline down
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        line["other_workloads"] = extra
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+KERNEL_ROLE = {  # which part of SURVEY.md 8(d)'s per-query byte formula a kernel covers
+    "sorted_count": "locate", "locate_count": "locate", "sorted_scatter": "sort", "scatter": "sort", "sorted_scan": "sort", "scan_leaves": "sort",
+    "sorted_eval": "eval", "eval_tensor_tiles": "eval", "eval_tiles": "eval", "mesh_tensor_mma": "eval", "mesh_tensor_tiles": "eval",
+    "mesh_gather": "eval", "weights": "eval", "eval_scalar_direct": "all", "eval_tensor_direct": "all", "jitter_points": "generate",
+    "error_reduce": "reduce", "mesh_nan_rows": "other", "checksum": "other",
+}
+
+
+def role_bytes_per_query(role, N, depth, T, K, D):
+    locate = 8 * N + 16 * depth + 5
+    evalb = T * (16 * N + 8 + 4) + K * D * 8 + 8 * D
+    return {"locate": locate, "sort": 2 * (8 * N + 8), "eval": evalb + 8 * N, "all": locate + evalb, "generate": 8 * N + 12, "reduce": 8 * D * 2 + 5}.get(role, 0)
+
+
+def measure(name, w, args, rank, world, local, config, full):
+    """one workload on this rank's GPU: timed steps (max over ranks), per-kernel CUDA-event times, roofline, e2e (full only)"""
+    import torch
+    import torch.distributed as dist
+    from locointerpolate_b200 import capi
+    steps = args.steps if full else max(2, min(args.steps, 3))
+    warmup = args.warmup if full else 3
     m, amp, phase = build_model(capi, w, local)
     m.set_option("path", args.path)
     m.set_option("chunk", args.chunk)
@@ -230,7 +273,7 @@ def main():
     if Q * (N + D) * 8 <= 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    if args.workload == "c5":
+    if name == "c5":
         err = torch.empty(info["n_leaves"], dtype=torch.float64, device="cuda")
         split = torch.empty(info["n_leaves"], dtype=torch.uint8, device="cuda")
         d_amp, d_phase = torch.from_numpy(amp).cuda(), torch.from_numpy(phase).cuda()
@@ -239,33 +282,33 @@ def main():
 
         def step(i):
             m.error_check_generated_device(ppl, 1000 + i, d_amp.data_ptr(), d_phase.data_ptr(), 10, 0.05, err.data_ptr(), split.data_ptr(), stream)
-        out_bytes = info["n_leaves"] * 9
     elif D == 1:
         outs = [torch.empty(Q, dtype=torch.float64, device="cuda") for _ in range(2)]
 
         def step(i):
             m.eval_device(q.data_ptr(), Q, outs[i % 2].data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
-        out_bytes = Q * 13
     else:
         # mesh-valued: the whole batch of results stays in HBM ([Q x D] doubles; sized for the 180 GB part)
-        stride = info["value_dim"] + (info["value_dim"] & 1)
-        mesh_out = torch.empty((Q, stride), dtype=torch.float64, device="cuda")
-        assert stride == D, "bench assumes an even value dimension"
+        assert D % 2 == 0, "bench assumes an even value dimension"
+        mesh_out = torch.empty((Q, D), dtype=torch.float64, device="cuda")
 
         def step(i):
             m.eval_device(q.data_ptr(), Q, mesh_out.data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
-        out_bytes = Q * (D * 8 + 5)
 
     gathered, handles = None, []
-    if world > 1 and D == 1 and args.workload != "c5":
+    if world > 1 and D == 1 and name != "c5":
         gathered = [torch.empty(world * Q, dtype=torch.float64, device="cuda") for _ in range(2)]
+    err_all = None
 
     def run(i):
         step(i)
         if gathered is not None:  # the path's one exchange step: gather the per-shard results (overlaps the next step)
             handles.append(dist.all_gather_into_tensor(gathered[i % 2], outs[i % 2], async_op=True))
+        elif world > 1 and name == "c5":  # error maxima: all_reduce(MAX) of the bit patterns + split flags (shard.py)
+            from locointerpolate_b200 import shard
+            shard.reduce_error_maxima(err, split)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         if flush is not None:
             flush.zero_()
         run(i)
@@ -277,14 +320,14 @@ def main():
         dist.barrier()
     launches0 = m.kernel_launches
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and full:
         sampler.start()
     t_wall = time.perf_counter()
     if flush is None:
         # inputs + outputs of a step exceed the L2: time the K steps back to back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             run(i)
         for h in handles:
             h.wait()
@@ -294,7 +337,7 @@ def main():
     else:
         # small batch: flush the L2 (write 256 MB) before every step, outside the timed events
         ms = 0.0
-        for i in range(args.steps):
+        for i in range(steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -308,46 +351,74 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and full else None
     launches = m.kernel_launches - launches0
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     value = world * Q / (ms_per_step * 1e-3)
-    bad = int((status != 0).sum().item()) if args.workload != "c5" else 0
+    bad = int((status != 0).sum().item()) if name != "c5" else 0
 
-    # ---- dominant kernel alone (no flush, no gather), CUDA events on the launching stream
-    ks = []
-    for i in range(max(3, args.steps)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); step(i); b.record(); torch.cuda.synchronize()
-        ks.append(a.elapsed_time(b))
-    kernel_ms = float(np.median(ks))
+    # ---- every kernel of the step, CUDA events around each launch on the launching stream (no flush, no gather)
+    m.profile_begin()
+    for i in range(steps):
+        step(i)
+    prof = m.profile_end()
+    tot_ms = sum(v["total_ms"] for v in prof.values()) or 1.0
+    kernels = {k: {"launches_per_step": v["launches"] / steps, "ms_per_launch": v["total_ms"] / v["launches"], "share": v["total_ms"] / tot_ms}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}
+    dom = next(iter(kernels))
+    dom_ms = kernels[dom]["ms_per_launch"]
+    q_per_launch = Q / kernels[dom]["launches_per_step"]
     T = info["n_terms"] / info["n_leaves"]
     K = info["n_support_entries"] / info["n_leaves"]
-    algo = algorithmic_bytes_per_query(N, info["depth"], T, K, D) * Q
+    role = KERNEL_ROLE.get(dom, "all")
+    algo_q = role_bytes_per_query(role, N, info["depth"], T, K, D)
+    algo = algo_q * q_per_launch
+    path_q = algorithmic_bytes_per_query(N, info["depth"], T, K, D)
     compulsory = Q * (8 * N + 8 * D + 5) + info["device_bytes"]
     peak, peak_src = measured_peak()
-    roofline = {"bound": "hbm", "achieved": algo / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": algo / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_query": algo / Q,
-                "compulsory": {"bytes_per_step": compulsory, "achieved_gbs": compulsory / (kernel_ms * 1e-3) / 1e9,
-                               "frac": compulsory / (kernel_ms * 1e-3) / 1e9 / peak},
-                "note": "algorithmic bytes count the reference's per-query data flow without caches (SURVEY.md 8d); terms and values are "
-                        "served from L2/shared memory here, so 'achieved' may exceed the HBM peak -- 'compulsory' is what must cross HBM"}
+    step_kernel_ms = tot_ms / steps
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(name, {})
+        if tj.get("kernel") == dom:
+            traffic = tj["dram_bytes_per_query"] * q_per_launch
+    roofline = {"bound": "hbm", "kernel": dom, "kernel_role": role, "achieved": algo / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": dom_ms, "queries_per_launch": q_per_launch, "algorithmic_bytes_per_query": algo_q,
+                "whole_path": {"algorithmic_bytes_per_query": path_q, "kernels_ms_per_step": step_kernel_ms,
+                               "achieved_gbs": path_q * Q / (step_kernel_ms * 1e-3) / 1e9},
+                "compulsory": {"bytes_per_step": compulsory, "achieved_gbs": compulsory / (step_kernel_ms * 1e-3) / 1e9,
+                               "frac": compulsory / (step_kernel_ms * 1e-3) / 1e9 / peak},
+                "fp64": {"flops_per_query": 2.0 * K * D, "achieved_tflops": 2.0 * K * D * Q / (step_kernel_ms * 1e-3) / 1e12, "peak_tflops": 36.4,
+                         "peak_source": "measured DFMA loop, tools/micro/dmma_rate.cu"} if D > 1 else None,
+                "note": "algorithmic bytes = SURVEY.md 8(d): the reference's per-query data flow without caches, restricted to the part the dominant "
+                        "kernel covers (kernel_role); leaf data is served from L1/L2/shared memory, so 'achieved' may exceed the HBM peak -- "
+                        "'compulsory' is what must cross HBM (queries in, results out, model once)"}
+
+    result = {"value": value, "unit": "queries/s", "ms_per_step": ms_per_step, "steps": steps, "queries_per_step_per_gpu": Q,
+              "gpu_launches": int(launches), "kernels": kernels, "roofline": roofline, "bad_status": bad,
+              "model": {k: info[k] for k in ("n_leaves", "n_samples", "n_terms", "max_support", "depth", "device_bytes")}}
+    if not full:
+        result["workload"] = f"{name}: {w['desc']}"
+        del q, leaf, status
+        m.free()
+        return result
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory; H2D + kernels + D2H inside)
     e2e = None
-    if args.workload != "c5" and not args.no_e2e:
+    if name != "c5" and not args.no_e2e:
         Qe = Q if D == 1 else min(Q, max(1, (4 << 30) // (D * 8)))
         hq = torch.empty((Qe, N), dtype=torch.float64).pin_memory()
         hq.copy_(q[:Qe].cpu())
         ho = torch.empty((Qe, D), dtype=torch.float64).pin_memory()
         hl = torch.empty(Qe, dtype=torch.int32).pin_memory()
         hs = torch.empty(Qe, dtype=torch.uint8).pin_memory()
-        n_e2e = max(2, min(args.steps, 3))
+        n_e2e = max(2, min(steps, 3))
         m.eval_raw(hq.data_ptr(), Qe, ho.data_ptr(), hl.data_ptr(), hs.data_ptr())
         if world > 1:
             dist.barrier()
@@ -364,20 +435,19 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[args.workload]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[name]
         try:
-            cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, args.workload)
+            cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, name)
         except SystemExit as e:
             cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port", "sample": str(e)}
 
-    if rank == 0:
-        print(json.dumps({"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                          "roofline": roofline, "cpu_baseline": cpu, "wall_s": wall, "bad_status": bad,
-                          "model": {k: info[k] for k in ("n_leaves", "n_samples", "n_terms", "max_support", "depth", "device_bytes")}}))
-    if world > 1:
-        dist.destroy_process_group()
+    line = {"metric": "interpolated_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels, "wall_s": wall, "bad_status": bad, "model": result["model"]}
+    del q, leaf, status
+    m.free()
+    return line
 
 
 if __name__ == "__main__":

@@ -212,10 +212,17 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
 /* ---- tuning / accounting -------------------------------------------------------------------------------- */
 /* options: "lut" 1 locate grid before the k-d descent (default) | 0 descent from the root only;
  *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
- *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto) */
+ *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto);
+ *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0) */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);
+
+/* per-kernel device times (CUDA events on the launching stream around every kernel this library launches, from any
+ * handle of this process) between begin and end; end synchronises the device and writes a JSON object
+ * {"kernel name": {"launches": n, "total_ms": t}, ...} into `json`. */
+int loco_profile_begin(loco_model_t *m);
+int loco_profile_end(loco_model_t *m, char *json, size_t cap);
 
 #ifdef __cplusplus
 }

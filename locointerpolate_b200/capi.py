@@ -79,6 +79,8 @@ SIGNATURES = {
     "loco_error_check_generated_device": (C.c_int, [_vp, _i64, C.c_uint64, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "loco_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "loco_kernel_launches": (_i64, [_vp]),
+    "loco_profile_begin": (C.c_int, [_vp]),
+    "loco_profile_end": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
 }
 
 
@@ -290,6 +292,16 @@ class Model:
     @property
     def kernel_launches(self) -> int:
         return lib().loco_kernel_launches(self._h)
+
+    def profile_begin(self):
+        self._check(lib().loco_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{kernel name: {"launches": n, "total_ms": t}} for every kernel launched since profile_begin (device synchronised)"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._check(lib().loco_profile_end(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def set_values(self, values):
         v = _np(values, np.float64).reshape(self.info["n_value_rows"], self.D)

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -18,6 +20,22 @@
 #include "loco_proto.h"
 
 using namespace loco;
+
+namespace loco {
+KernelProfile &kernel_profile()
+{
+	static KernelProfile p;
+	return p;
+}
+void KernelProfile::push(const char *name, cudaEvent_t a, cudaEvent_t b)
+{
+	if (n == cap) {
+		cap = cap ? cap * 2 : 1024;
+		recs = static_cast<Rec *>(realloc(recs, sizeof(Rec) * (size_t)cap));
+	}
+	recs[n++] = Rec{name, a, b};
+}
+} // namespace loco
 
 namespace {
 
@@ -48,7 +66,7 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 };
@@ -299,8 +317,14 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
 		if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
 		const SortWork sw = carve_sort_work(dm, Q, w.misc);
-		m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_tile_queries(), nullptr, st);
-		m->launches += launch_mesh_tensor_tiles(dm, sw, status, Q, out, out_stride, m->sm_count, st);
+		if (mesh_mma_supported(dm) && !m->opt_mesh_simt) {
+			m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_mma_tile_queries(), nullptr, st);
+			m->launches += launch_mesh_tensor_mma(dm, sw, Q, out, out_stride, m->sm_count, st);
+			m->launches += launch_mesh_nan_rows(dm, status, Q, out, out_stride, st);
+		} else {
+			m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_tile_queries(), nullptr, st);
+			m->launches += launch_mesh_tensor_tiles(dm, sw, status, Q, out, out_stride, m->sm_count, st);
+		}
 		CUDA_OK(m, cudaGetLastError());
 		return LOCO_OK;
 	}
@@ -761,6 +785,7 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!m || !name) return fail(m, LOCO_ERR_INVALID, "null argument");
 	if (!strcmp(name, "path")) { m->opt_path = value; return LOCO_OK; }
 	if (!strcmp(name, "fp32")) { m->opt_fp32 = value; return LOCO_OK; }
+	if (!strcmp(name, "mesh_simt")) { m->opt_mesh_simt = value; return LOCO_OK; }  // 1: DFMA register-tile mesh kernel instead of the fp64 MMA one
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
 	if (!strcmp(name, "lut")) {  // 0: plain k-d descent from the root, 1: locate grid first (default)
 		if (m->dm.lut) m->d_lut = m->dm.lut;
@@ -772,5 +797,48 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 }
 
 int64_t loco_kernel_launches(const loco_model_t *m) { return m ? m->launches : 0; }
+
+int loco_profile_begin(loco_model_t *m)
+{
+	if (!m) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	KernelProfile &p = kernel_profile();
+	for (int i = 0; i < p.n; i++) { cudaEventDestroy(p.recs[i].a); cudaEventDestroy(p.recs[i].b); }
+	p.n = 0;
+	p.on = true;
+	return LOCO_OK;
+}
+
+int loco_profile_end(loco_model_t *m, char *json, size_t cap)
+{
+	if (!m || !json || cap < 2) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	KernelProfile &p = kernel_profile();
+	p.on = false;
+	CUDA_OK(m, cudaSetDevice(m->device));
+	CUDA_OK(m, cudaDeviceSynchronize());
+	struct Agg { const char *name; int64_t n; double ms; };
+	std::vector<Agg> agg;
+	for (int i = 0; i < p.n; i++) {
+		float ms = 0;
+		cudaEventElapsedTime(&ms, p.recs[i].a, p.recs[i].b);
+		cudaEventDestroy(p.recs[i].a); cudaEventDestroy(p.recs[i].b);
+		size_t k = 0;
+		for (; k < agg.size(); k++) if (!strcmp(agg[k].name, p.recs[i].name)) break;
+		if (k == agg.size()) agg.push_back(Agg{p.recs[i].name, 0, 0.0});
+		agg[k].n++; agg[k].ms += ms;
+	}
+	p.n = 0;
+	std::string out = "{";
+	for (size_t k = 0; k < agg.size(); k++) {
+		char buf[256];
+		snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %lld, \"total_ms\": %.6f}", k ? ", " : "", agg[k].name, (long long)agg[k].n, agg[k].ms);
+		out += buf;
+	}
+	out += "}";
+	if (out.size() + 1 > cap) return fail(m, LOCO_ERR_RANGE, "profile buffer too small");
+	memcpy(json, out.c_str(), out.size() + 1);
+	return LOCO_OK;
+}
 
 } // extern "C"

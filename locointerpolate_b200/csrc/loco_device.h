@@ -53,6 +53,37 @@ struct DeviceModel {
 };
 
 
+// ---- per-kernel timing (bench.py's roofline leg): CUDA events around every launch of a named kernel, recorded on
+// the launching stream while profiling is switched on (loco_profile_begin / loco_profile_end)
+struct KernelProfile {
+	bool on = false;
+	struct Rec { const char *name; cudaEvent_t a, b; };
+	Rec *recs = nullptr;
+	int n = 0, cap = 0;
+	void push(const char *name, cudaEvent_t a, cudaEvent_t b);
+};
+KernelProfile &kernel_profile();
+struct ScopedKernelTime {
+	cudaEvent_t a = nullptr, b = nullptr;
+	cudaStream_t st;
+	const char *name;
+	ScopedKernelTime(const char *name_, cudaStream_t st_) : st(st_), name(name_)
+	{
+		if (!kernel_profile().on) return;
+		cudaEventCreate(&a); cudaEventCreate(&b);
+		cudaEventRecord(a, st);
+	}
+	~ScopedKernelTime()
+	{
+		if (!a) return;
+		cudaEventRecord(b, st);
+		kernel_profile().push(name, a, b);
+	}
+};
+#define LOCO_KERNEL_CAT2(a, b) a##b
+#define LOCO_KERNEL_CAT(a, b) LOCO_KERNEL_CAT2(a, b)
+#define LOCO_KERNEL(name, st) ::loco::ScopedKernelTime LOCO_KERNEL_CAT(_loco_kt_, __LINE__)(name, st)
+
 // ---- launchers (loco_kernels.cu).  All asynchronous on `st`; return the number of kernels launched.
 // fused map -> locate -> weights -> weighted sum for scalar functions (D == 1), one thread per query
 int launch_eval_scalar_direct(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf,
@@ -103,6 +134,11 @@ int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_
 int mesh_tile_queries();
 int launch_mesh_tensor_tiles(const DeviceModel &m, const SortWork &w, const uint8_t *status, int64_t Q, double *out, int64_t out_stride, int sm_count,
                              cudaStream_t st);
+int launch_mesh_nan_rows(const DeviceModel &m, const uint8_t *status, int64_t Q, double *out, int64_t out_stride, cudaStream_t st);
+// fp64 MMA version of the mesh tile kernel (loco_mesh_mma.cu); same sorted input, tiles of mesh_mma_tile_queries()
+int mesh_mma_tile_queries();
+bool mesh_mma_supported(const DeviceModel &m);
+int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
 

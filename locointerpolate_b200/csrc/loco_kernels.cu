@@ -354,6 +354,7 @@ template <int NT, bool CUBIC, bool EXACT, bool IN_CUBE>
 struct EvalScalarLauncher {
 	static void run(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
 	{
+		LOCO_KERNEL("eval_scalar_direct", st);
 		eval_scalar_direct_kernel<NT, CUBIC, EXACT, IN_CUBE><<<blocks_for(Q, 256), 256, 0, st>>>(m, q, Q, out, leaf, status);
 	}
 };
@@ -361,6 +362,7 @@ template <int NT, bool CUBIC, bool EXACT, bool IN_CUBE>
 struct WeightsLauncher {
 	static void run(const DeviceModel &m, const double *q, int64_t Q, double *W, int32_t *leaf, uint8_t *status, cudaStream_t st)
 	{
+		LOCO_KERNEL("weights", st);
 		weights_kernel<NT, CUBIC, EXACT, IN_CUBE><<<blocks_for(Q, 256), 256, 0, st>>>(m, q, Q, W, leaf, status);
 	}
 };
@@ -368,6 +370,7 @@ template <int NT, bool CUBIC, bool EXACT, bool UNUSED>
 struct EvalDerivLauncher {
 	static void run(const DeviceModel &m, const double *q, int64_t Q, int direction, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
 	{
+		LOCO_KERNEL("eval_deriv_direct", st);
 		eval_deriv_direct_kernel<NT, CUBIC, EXACT, UNUSED><<<blocks_for(Q, 256), 256, 0, st>>>(m, q, Q, direction, out, leaf, status);
 	}
 };
@@ -430,6 +433,7 @@ int launch_mesh_gather(const DeviceModel &m, const double *W, const int32_t *lea
 	if (Q <= 0) return 0;
 	size_t smem = (size_t)m.max_support * (sizeof(double) + sizeof(int32_t)) + 16;
 	if (smem > 48 * 1024) cudaFuncSetAttribute(mesh_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	LOCO_KERNEL("mesh_gather", st);
 	mesh_gather_kernel<<<(unsigned)Q, 256, smem, st>>>(m, W, leaf, status, out, out_stride);
 	return 1;
 }
@@ -437,6 +441,7 @@ int launch_mesh_gather(const DeviceModel &m, const double *W, const int32_t *lea
 int launch_checksum(const double *out, int64_t out_stride, int32_t D, int64_t Q, double *checksum, cudaStream_t st)
 {
 	if (Q <= 0) return 0;
+	LOCO_KERNEL("checksum", st);
 	checksum_kernel<<<(unsigned)Q, 256, 0, st>>>(out, out_stride, D, checksum);
 	return 1;
 }
@@ -445,6 +450,7 @@ int launch_error_reduce(const DeviceModel &m, const double *out, const double *t
                         double threshold, double *err_max, uint8_t *split, unsigned long long *n_bad, cudaStream_t st)
 {
 	if (P <= 0) return 0;
+	LOCO_KERNEL("error_reduce", st);
 	error_reduce_kernel<<<blocks_for(P, 256), 256, 0, st>>>(m, out, truth, leaf, status, P, threshold,
 	                                                       reinterpret_cast<unsigned long long *>(err_max), split, n_bad);
 	return 1;
@@ -474,6 +480,7 @@ int launch_jitter_points(const DeviceModel &m, int64_t points_per_leaf, uint64_t
                          const double *phase, int32_t n_terms, double *q_out, int32_t *leaf_out, double *truth_out, cudaStream_t st)
 {
 	if (count <= 0) return 0;
+	LOCO_KERNEL("jitter_points", st);
 	jitter_points_kernel<<<blocks_for(count, 256), 256, 0, st>>>(m, points_per_leaf, seed, first, count, amp, phase, n_terms, q_out, leaf_out, truth_out);
 	return 1;
 }

@@ -197,6 +197,14 @@ __global__ void __launch_bounds__(256) mesh_nan_rows_kernel(const uint8_t *__res
 	(void)Q;
 }
 
+int launch_mesh_nan_rows(const DeviceModel &m, const uint8_t *status, int64_t Q, double *out, int64_t out_stride, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	LOCO_KERNEL("mesh_nan_rows", st);
+	mesh_nan_rows_kernel<<<(unsigned)Q, 256, 0, st>>>(status, Q, m.D, out, out_stride);
+	return 1;
+}
+
 size_t mesh_tiles_smem_bytes(int N, int F)
 {
 	return (size_t)(2 * MT_K * MT_D + 2 * MT_K * MT_Q + N * F * MT_Q) * sizeof(double) + MT_Q * sizeof(int32_t) + 64;
@@ -210,6 +218,7 @@ void run_mesh(const DeviceModel &m, const SortWork &w, double *out, int64_t out_
 	auto kern = mesh_tensor_tiles_kernel<NT, CUBIC, EXACT>;
 	const size_t smem = mesh_tiles_smem_bytes(NT, CUBIC ? 4 : 2);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	LOCO_KERNEL("mesh_tensor_tiles", st);
 	kern<<<grid, MT_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, out, out_stride, n_dchunks);
 }
 } // namespace
@@ -229,8 +238,7 @@ int launch_mesh_tensor_tiles(const DeviceModel &m, const SortWork &w, const uint
 		break;
 	switch (m.N) { LOCO_MCASE(1) LOCO_MCASE(2) LOCO_MCASE(3) LOCO_MCASE(4) LOCO_MCASE(5) LOCO_MCASE(6) LOCO_MCASE(7) LOCO_MCASE(8) default: return 0; }
 #undef LOCO_MCASE
-	mesh_nan_rows_kernel<<<(unsigned)Q, 256, 0, st>>>(status, Q, m.D, out, out_stride);
-	return 2;
+	return 1 + launch_mesh_nan_rows(m, status, Q, out, out_stride, st);
 }
 
 } // namespace loco

@@ -227,18 +227,22 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 template <int NT>
 void run_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, double *out, const SortedWork &w, cudaStream_t st)
 {
-	sorted_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count);
+	{ LOCO_KERNEL("sorted_count", st);
+	sorted_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
+	LOCO_KERNEL("sorted_scan", st);
 	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, m.L);
 }
 template <int NT>
 void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortedWork &w, cudaStream_t st)
 {
+	LOCO_KERNEL("sorted_scatter", st);
 	sorted_scatter_kernel<NT><<<(unsigned)((Q + 256 * kScatterItems - 1) / (256 * kScatterItems)), 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
 }
 template <int NT, bool CUBIC, bool EXACT>
 void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, cudaStream_t st)
 {
 	const unsigned g = (unsigned)std::min<int64_t>((Q + 255) / 256, (int64_t)sm_count * 8);
+	LOCO_KERNEL("sorted_eval", st);
 	if constexpr (NT > 0) {
 		if (m.tensor_F > 0) { sorted_eval_kernel<NT, CUBIC, EXACT, true><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
 	}

@@ -58,6 +58,7 @@ template <int NT, bool IN_CUBE>
 void run(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, cudaStream_t st)
 {
 	const unsigned g = (unsigned)((Q + 255) / 256);
+	LOCO_KERNEL("eval_tensor_direct", st);
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 	if (cubic) {
 		if (exact) eval_tensor_direct_kernel<NT, true, true, IN_CUBE><<<g, 256, 0, st>>>(m, q, Q, out, leaf, status);

@@ -301,11 +301,13 @@ const int kTileQ = 128;
 template <int NT>
 void locate_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, double *out, cudaStream_t st)
 {
+	LOCO_KERNEL("locate_count", st);
 	locate_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, w.count, w.rank, out);
 }
 template <int NT>
 void scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortWork &w, cudaStream_t st)
 {
+	LOCO_KERNEL("scatter", st);
 	scatter_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, leaf, status, w.rank, Q, w.offset, w.idx, w.xs);
 }
 
@@ -315,6 +317,7 @@ void eval_tensor_tiles(const DeviceModel &m, const double *q, double *out, const
 	auto kern = eval_tensor_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
 	const size_t smem = (size_t)m.tl_stride * 8 * 2;
 	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	LOCO_KERNEL("eval_tensor_tiles", st);
 	kern<<<grid, kTileQ, smem, st>>>(m, w.xs, out, w.offset, w.tile_off, w.idx);
 }
 
@@ -322,6 +325,7 @@ template <int NT, bool CUBIC, bool EXACT>
 void eval_tiles(const DeviceModel &m, const double *q, double *out, const SortWork &w, int chunk_terms, size_t smem, int grid, cudaStream_t st)
 {
 	auto kern = eval_tiles_kernel<NT, CUBIC, EXACT, kTileQ>;
+	LOCO_KERNEL("eval_tiles", st);
 	kern<<<grid, kTileQ, smem, st>>>(m, w.xs, out, w.offset, w.tile_off, w.idx, chunk_terms);
 }
 } // namespace
@@ -370,7 +374,8 @@ int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_
 	case 8: locate_count<8>(m, q, Q, leaf, status, w, out, st); break;
 	default: locate_count<0>(m, q, Q, leaf, status, w, out, st); break;
 	}
-	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, tile_q, w.offset, w.tile_off);
+	{ LOCO_KERNEL("scan_leaves", st);
+	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, tile_q, w.offset, w.tile_off); }
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 	case 1: scatter<1>(m, q, Q, leaf, status, w, st); break;
 	case 2: scatter<2>(m, q, Q, leaf, status, w, st); break;

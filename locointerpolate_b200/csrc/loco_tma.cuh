@@ -26,6 +26,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		    : "=r"(done) : "r"(addr), "r"(parity) : "memory");
 	}
 }
+// plain arrival (release semantics at CTA scope: the arriving thread's earlier shared-memory writes are visible to
+// threads that observe the phase completion with mbar_wait)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy executed by the TMA engine; size and both addresses are multiples of 16 B
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {

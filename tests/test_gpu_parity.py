@@ -82,12 +82,14 @@ def test_mesh_valued(golden, name, D):
     m = capi.Model.from_graph(g, device=0)
     orc = oracleapi.Oracle(g)
     q = z["q"][:400]
-    out, leaf, status = m.eval(q)
     o_out, o_leaf, o_status, scale = orc.eval(q)
-    assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
-    ok = status == 0
-    assert_values_close(out[ok], o_out[ok], scale[ok])
-    assert np.isnan(out[~ok]).all()
+    for simt in (0, 1):  # fp64 MMA tiles (default) and DFMA register tiles
+        m.set_option("mesh_simt", simt)
+        out, leaf, status = m.eval(q)
+        assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
+        ok = status == 0
+        assert_values_close(out[ok], o_out[ok], scale[ok])
+        assert np.isnan(out[~ok]).all()
 
 
 def test_error_check_matches_oracle(golden):
