@@ -214,6 +214,11 @@ int build_device_model(loco_model *m)
 		m->d_tl_block = const_cast<double *>(dblk);
 		dm.tl_block = dblk;
 		if ((rc = upload(m, f.tl_row, &dm.tl_row))) return rc;
+		std::vector<int32_t> fold_off = narrow(m, f.fold_off, &ok);
+		if ((rc = upload(m, fold_off, &dm.fold_off))) return rc;
+		if ((rc = upload(m, f.fold_row, &dm.fold_row))) return rc;
+		if ((rc = upload(m, f.fold_map, &dm.fold_map))) return rc;
+		if ((rc = upload(m, f.fold_n, &dm.fold_n))) return rc;
 	}
 	dm.dom_exact_mask = 0;
 	for (int d = 0; d < f.N; d++) {

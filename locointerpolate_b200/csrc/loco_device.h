@@ -47,6 +47,11 @@ struct DeviceModel {
 	const double *lut_bounds;
 	int32_t lut_bits[kMaxN], lut_boff[kMaxN];
 	double lut_lo[kMaxN], lut_inv[kMaxN];   // estimate of the grid cell: (x - lo) * inv, then exact comparisons
+	// folded tensor leaves (Flat::fold_*): value rows after merging digits that share rows
+	const int32_t *fold_off;          // [L+1]
+	const int32_t *fold_row;
+	const uint8_t *fold_map;          // [L*N*F]
+	const uint8_t *fold_n;            // [L*N]
 	// containment against the root box only (valid when every leaf box is implied by its split planes)
 	int32_t path_consistent, any_leaf_status;
 	double root_lo_eps[kMaxN], root_hi_eps[kMaxN];

@@ -89,6 +89,18 @@ struct Flat {
 	std::vector<int32_t> tl_slot;         // [L * F^N]   slot in the leaf's sorted support list, tensor order (dimension 0 fastest)
 	std::vector<int32_t> tl_row;          // [L * F^N]   value row, same order
 
+	// ---- folded tensor leaves (mesh-valued path) --------------------------------------------------------------------
+	// Samples that share one LCFunctionValue object (cubic border samples built with evalCorners=false share the value
+	// of their clamped in-domain sample, LCAdaptiveGrid.cpp:345-355) carry the same value row.  On a tensor leaf that
+	// sharing is itself a tensor product: in dimension d, digits j and j' are equivalent when swapping them never changes
+	// the row.  Then  sum_k w_k V[row_k]  =  sum over CLASSES of (prod_d g_d[class_d]) V[row],  g_d[c] = sum of the
+	// factors of the digits in class c -- the same sum re-associated, with prod_d n_d instead of F^N rows.
+	std::vector<int64_t> fold_off;        // [L+1] CSR into fold_row
+	std::vector<int32_t> fold_row;        // value rows of the folded tensor, class index of dimension 0 fastest
+	std::vector<uint8_t> fold_map;        // [L * N * F] digit -> class index in its dimension
+	std::vector<uint8_t> fold_n;          // [L * N] classes per dimension (1..F)
+	int32_t max_fold_K = 0;
+
 	// every leaf box equals the box implied by the split planes on its root path: the +-EPSILON containment
 	// test can then only fail at the root box, and no per-leaf bounds need to be read per query
 	bool path_consistent = false;

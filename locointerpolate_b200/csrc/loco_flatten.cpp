@@ -333,6 +333,50 @@ Status flatten(const Graph &g, Flat *out)
 		}
 		if (all) { f.tensor_F = F; f.tensor_K = (int32_t)KT; }
 		else { f.tl_center.clear(); f.tl_rcp.clear(); f.tl_slot.clear(); f.tl_row.clear(); }
+		// ---- fold digits whose exchange never changes the value row (see loco_flat.h)
+		if (all) {
+			f.fold_off.assign(1, 0);
+			f.fold_map.resize((size_t)L * N * F);
+			f.fold_n.resize((size_t)L * N);
+			std::vector<int64_t> stride((size_t)N);
+			for (int i = 0; i < N; i++) stride[(size_t)i] = i ? stride[(size_t)i - 1] * F : 1;
+			for (int64_t l = 0; l < L; l++) {
+				const int32_t *rows = &f.tl_row[(size_t)l * KT];
+				uint8_t *map = &f.fold_map[(size_t)l * N * F];
+				int rep[16][4];  // representative digit of each class
+				for (int d = 0; d < N; d++) {
+					int n = 0;
+					for (int j = 0; j < F; j++) {
+						int cls = -1;
+						for (int c = 0; c < n && cls < 0; c++) {
+							// j ~ rep[d][c]  iff  rows agree for every setting of the other digits
+							const int64_t dj = (int64_t)(j - rep[d][c]) * stride[(size_t)d];
+							bool same = true;
+							for (int64_t k = 0; k < KT && same; k++)
+								if ((k / stride[(size_t)d]) % F == rep[d][c]) same = rows[k] == rows[k + dj];
+							if (same) cls = c;
+						}
+						if (cls < 0) { cls = n; rep[d][n++] = j; }
+						map[d * F + j] = (uint8_t)cls;
+					}
+					f.fold_n[(size_t)l * N + d] = (uint8_t)n;
+				}
+				// rows of the folded tensor (representatives), class index of dimension 0 fastest
+				int64_t KF = 1;
+				for (int d = 0; d < N; d++) KF *= f.fold_n[(size_t)l * N + d];
+				for (int64_t kf = 0; kf < KF; kf++) {
+					int64_t r = kf, k = 0;
+					for (int d = 0; d < N; d++) {
+						const int n = f.fold_n[(size_t)l * N + d];
+						k += rep[d][r % n] * stride[(size_t)d];
+						r /= n;
+					}
+					f.fold_row.push_back(rows[k]);
+				}
+				f.fold_off.push_back((int64_t)f.fold_row.size());
+				f.max_fold_K = std::max<int32_t>(f.max_fold_K, (int32_t)KF);
+			}
+		}
 	}
 
 	// ---- are the leaf boxes exactly the boxes implied by the split planes? -----------------------------------

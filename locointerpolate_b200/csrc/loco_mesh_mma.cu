@@ -25,6 +25,7 @@
 // Items are ordered chunk-group major and dealt round-robin to the CTAs, so that at any time all CTAs read the same
 // slice of the value table (it stays L2 resident: the table is read from HBM about once per batch).
 #include <algorithm>
+#include <cstdlib>
 
 #include "loco_basis.cuh"
 #include "loco_device.h"
@@ -37,7 +38,8 @@ namespace {
 constexpr int MM_Q = 64;      // queries per tile
 constexpr int MM_D = 128;     // value components per chunk
 constexpr int MM_K = 16;      // value rows per stage
-constexpr int MM_NS = 3;      // stages in flight (2 CTAs of ~98 KB per SM)
+constexpr int MM_NS_MULTI = 3; // stages in flight when a chunk needs several stages (2 CTAs of ~98 KB per SM)
+constexpr int MM_NS_ONE = 4;   // ... when all K <= 16 rows fit one stage: the weights are per item, a stage is value rows only
 constexpr int MM_CONSUMERS = 8;
 constexpr int MM_PRODUCERS = MM_Q / 32;  // one producer lane per query of the tile
 constexpr int MM_THREADS = (MM_CONSUMERS + MM_PRODUCERS) * 32;
@@ -49,10 +51,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc; };
+struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc, row0, K; };  // row0, K: the leaf's folded row list in DeviceModel::fold_row
 // item -> (chunk group, tile) -> leaf and query range; identical arithmetic in the producer and in every consumer warp
 __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t n_tiles, int32_t L, int32_t n_dchunks, int dg, const int32_t *__restrict__ offset,
-                                                  const int32_t *__restrict__ tile_off)
+                                                  const int32_t *__restrict__ tile_off, const int32_t *__restrict__ fold_off)
 {
 	ItemGeom g;
 	const int64_t dgroup = item / n_tiles, tile = item - dgroup * n_tiles;
@@ -66,11 +68,13 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t n_tiles,
 	g.nq = min(MM_Q, __ldg(offset + lo + 1) - g.qbeg);
 	g.dc0 = (int32_t)dgroup * dg;
 	g.n_dc = min(dg, n_dchunks - g.dc0);
+	g.row0 = __ldg(fold_off + lo);
+	g.K = __ldg(fold_off + lo + 1) - g.row0;
 	return g;
 }
 } // namespace
 
-template <int NT, bool CUBIC, bool EXACT>
+template <int NT, bool CUBIC, bool EXACT, bool ONE>
 __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceModel m, const double *__restrict__ xs, const int32_t *__restrict__ offset,
                                                                          const int32_t *__restrict__ tile_off, double *__restrict__ out,
                                                                          int64_t out_stride, int32_t n_dchunks, int32_t dg)
@@ -82,10 +86,12 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	// "high" product is constant over runs of LOWK consecutive rows
 	constexpr int LOWD = NT < (CUBIC ? 2 : 4) ? NT : (CUBIC ? 2 : 4);
 	constexpr int LOWK = 1 << (LOGF * LOWD);
+	constexpr int MM_NS = ONE ? MM_NS_ONE : MM_NS_MULTI;
+	constexpr int MM_NW = ONE ? 2 : MM_NS;  // weight buffers: per item (ONE) or per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *sV = reinterpret_cast<double *>(smem_raw);             // [MM_NS][MM_K][MM_LDV]
-	double *sW = sV + MM_NS * MM_K * MM_LDV;                       // [MM_NS][MM_K][MM_LDW]
-	double *sF = sW + MM_NS * MM_K * MM_LDW;                       // [NT*F][MM_Q]   producer only
+	double *sW = sV + MM_NS * MM_K * MM_LDV;                       // [MM_NW][MM_K][MM_LDW]
+	double *sF = sW + MM_NW * MM_K * MM_LDW;                       // [NT*F][MM_Q]   producer only
 	double *sL = sF + NT * F * MM_Q;                               // [LOWK][MM_Q]   producer only
 	int32_t *sQi = reinterpret_cast<int32_t *>(sL + LOWK * MM_Q);  // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
 	__shared__ __align__(8) uint64_t full_bar[MM_NS], empty_bar[MM_NS], item_bar[2];
@@ -95,21 +101,21 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	}
 	__syncthreads();
 
-	const int32_t L = m.L, K = m.tensor_K;
+	const int32_t L = m.L;
 	const int64_t n_tiles = tile_off[L];
 	const int32_t n_dgroups = (n_dchunks + dg - 1) / dg;
 	const int64_t total = n_tiles * n_dgroups;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n_stages = (K + MM_K - 1) / MM_K;
 
 	if (warp >= MM_CONSUMERS) {
 		// ========================================== producer warps ===========================================
 		// lane owns ONE query of the tile (q = 32 * producer index + lane); producer 0 also drives the TMA engine
 		const int pw = warp - MM_CONSUMERS, q = pw * 32 + lane;
+		const uint64_t keep = l2_policy_evict_last();  // the slice of the value table all CTAs share stays in L2 under the result stream
 		uint32_t g = 0;   // running step counter: stage = g % MM_NS, use count = g / MM_NS
 		uint32_t it = 0;  // running item counter: item buffer = it & 1
 		for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-			const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off);
+			const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
 			const int ib = it & 1;
 			// the consumers are done with this item buffer (two items ago); a fresh barrier passes the parity-1 wait
 			mbar_wait(&item_bar[ib], ((it >> 1) & 1u) ^ 1u);
@@ -123,58 +129,116 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 			sQi[ib * MM_Q + q] = qi;
 			double f[NT][F];
 			tensor_factors<NT, CUBIC, EXACT>(blk, x, f);
-			// ---- products over the low dimensions, kept in shared memory (column q is private to this lane)
+			// ---- folded factors g[d][c] = sum of the factors of the digits in class c (DeviceModel::fold_map), kept in shared
+			//      memory (column q is private to this lane) so that they can be indexed by a runtime class index
+			const uint8_t *fmap = m.fold_map + (int64_t)ig.leaf * NT * F;
+			const uint8_t *fnum = m.fold_n + (int64_t)ig.leaf * NT;
+			int nd[NT];
 #pragma unroll
-			for (int kl = 0; kl < LOWK; kl++) {
-				double w = q < ig.nq ? 1.0 : 0.0;
-				int k = kl;
+			for (int d = 0; d < NT; d++) {
+				nd[d] = __ldg(fnum + d);
+				double gsum[F];
 #pragma unroll
-				for (int d = 0; d < LOWD; d++) { w *= f[d][k & (F - 1)]; k >>= LOGF; }
-				sL[kl * MM_Q + q] = w;
+				for (int c = 0; c < F; c++) gsum[c] = 0.0;
+#pragma unroll
+				for (int j = 0; j < F; j++) {
+					const int cls = __ldg(fmap + d * F + j);
+#pragma unroll
+					for (int c = 0; c < F; c++) gsum[c] += (cls == c) ? f[d][j] : 0.0;
+				}
+#pragma unroll
+				for (int c = 0; c < F; c++) sF[(d * F + c) * MM_Q + q] = q < ig.nq ? gsum[c] : 0.0;
 			}
+			// ---- products over the low dimensions (mixed radix nd[0..LOWD)): sL[kl][q], kl < lowK <= 16
+			int lowK = 1;
 #pragma unroll
-			for (int d = LOWD; d < NT; d++)
+			for (int d = 0; d < LOWD; d++) lowK *= nd[d];
+			{
+				int dig[LOWD];
 #pragma unroll
-				for (int j = 0; j < F; j++) sF[(d * F + j) * MM_Q + q] = f[d][j];
-			const int32_t *rows = m.tl_row + (int64_t)ig.leaf * K;
+				for (int d = 0; d < LOWD; d++) dig[d] = 0;
+				for (int kl = 0; kl < lowK; kl++) {
+					double w = 1.0;
+#pragma unroll
+					for (int d = 0; d < LOWD; d++) w *= sF[(d * F + dig[d]) * MM_Q + q];
+					sL[kl * MM_Q + q] = w;
+#pragma unroll
+					for (int d = 0; d < LOWD; d++) {  // increment the mixed-radix counter
+						if (++dig[d] < nd[d]) break;
+						dig[d] = 0;
+					}
+				}
+			}
+			const int32_t K = ig.K;
+			const int n_stages = (K + MM_K - 1) / MM_K;
+			const int32_t *rows = m.fold_row + ig.row0;
 			const int n_steps = ig.n_dc * n_stages;
 			// everything a step needs that does not depend on the stage being free is prepared BEFORE waiting for it:
-			// the row index of this lane's TMA copy (a global load) and the 16 weights (kept in registers)
-			int32_t my_row = (lane < min(MM_K, K)) ? __ldg(rows + lane) : 0;
+			// the row index of this lane's TMA copy (a global load) and the 16 weights (kept in registers).
+			// Rows are padded to a multiple of 4 per stage with zero weights (the MMA consumes 4 rows at a time); the
+			// padding lanes copy the leaf's last row so that 0 * value stays finite.
+			auto row_of = [&](int c, int ln) -> int32_t {
+				const int kc4 = (min(MM_K, K - c * MM_K) + 3) & ~3;
+				return ln < kc4 ? __ldg(rows + min(c * MM_K + ln, K - 1)) : 0;
+			};
+			int32_t my_row = row_of(0, lane);
+			if (ONE) {
+				// all rows fit one stage: the weights do not depend on the chunk, write them once per item (item buffer ib;
+				// the first stage barrier of the item publishes them)
+				double *W_ = sW + (size_t)ib * MM_K * MM_LDW + q;
+#pragma unroll
+				for (int kk = 0; kk < MM_K; kk++) W_[kk * MM_LDW] = kk < K ? sL[kk * MM_Q + q] : 0.0;
+			}
 			for (int s = 0; s < n_steps; s++, g++) {
 				const int dc = s / n_stages, c = s - dc * n_stages;
 				const int st = g % MM_NS;
-				const int kc = min(MM_K, K - c * MM_K);
-				// ---- weights of the stage: w[kk] = low[k % LOWK] * high(k / LOWK).  With more than LOWD dimensions LOWK == MM_K, so the
-				//      high product is one number per stage (high index = c); otherwise there are no high dimensions at all
-				double ph = 1.0;
-				if (NT > LOWD) {
-					int hh = c;
+				const int kc = min(MM_K, K - c * MM_K), kc4 = (kc + 3) & ~3;
+				// ---- weights of the stage: w[kk] = low[k % lowK] * high(k / lowK), k = c*MM_K + kk, walked incrementally
+				double wreg[ONE ? 1 : MM_K];
+				if (!ONE) {
+					int low = (c * MM_K) % lowK, high = (c * MM_K) / lowK;
+					int hd[NT > LOWD ? NT - LOWD : 1];
 #pragma unroll
-					for (int d = LOWD; d < NT; d++) { ph *= sF[(d * F + (hh & (F - 1))) * MM_Q + q]; hh >>= LOGF; }
+					for (int d = LOWD; d < NT; d++) { hd[d - LOWD] = high % nd[d]; high /= nd[d]; }
+					auto high_product = [&]() {
+						double p = 1.0;
+#pragma unroll
+						for (int d = LOWD; d < NT; d++) p *= sF[(d * F + hd[d - LOWD]) * MM_Q + q];
+						return p;
+					};
+					double ph = high_product();
+#pragma unroll
+					for (int kk = 0; kk < MM_K; kk++) {
+						wreg[kk] = kk < kc ? sL[low * MM_Q + q] * ph : 0.0;
+						if (++low == lowK) {
+							low = 0;
+#pragma unroll
+							for (int d = LOWD; d < NT; d++) {
+								if (++hd[d - LOWD] < nd[d]) break;
+								hd[d - LOWD] = 0;
+							}
+							ph = high_product();
+						}
+					}
 				}
-				double wreg[MM_K];
-#pragma unroll
-				for (int kk = 0; kk < MM_K; kk++) wreg[kk] = sL[(kk & (LOWK - 1)) * MM_Q + q] * ph;
 				const int32_t row = my_row;
-				if (pw == 0 && s + 1 < n_steps) {  // row index of the NEXT step's copy
-					const int c1 = (c + 1 == n_stages) ? 0 : c + 1;
-					my_row = (lane < min(MM_K, K - c1 * MM_K)) ? __ldg(rows + c1 * MM_K + lane) : 0;
-				}
+				if (pw == 0 && s + 1 < n_steps) my_row = row_of((c + 1 == n_stages) ? 0 : c + 1, lane);  // row index of the NEXT step's copy
 				mbar_wait(&empty_bar[st], ((g / MM_NS) & 1u) ^ 1u);
-				double *W_ = sW + (size_t)st * MM_K * MM_LDW + q;
+				if (!ONE) {
+					double *W_ = sW + (size_t)st * MM_K * MM_LDW + q;
 #pragma unroll
-				for (int kk = 0; kk < MM_K; kk++)
-					if (kk < kc) W_[kk * MM_LDW] = wreg[kk];
+					for (int kk = 0; kk < MM_K; kk++)
+						if (kk < kc4) W_[kk * MM_LDW] = wreg[kk];
+				}
 				__syncwarp();  // every lane's weights are written before lane 0 arrives on the stage barrier
 				if (pw == 0) {
 					// ---- the stage's value rows: one TMA bulk copy per row segment
 					const int32_t d0 = (ig.dc0 + dc) * MM_D;
 					const uint32_t row_bytes = (uint32_t)(((min(MM_D, m.D - d0) + 1) & ~1) * 8);  // rows are padded to an even number of doubles
-					if (lane == 0) mbar_expect_tx(&full_bar[st], row_bytes * (uint32_t)kc);
+					if (lane == 0) mbar_expect_tx(&full_bar[st], row_bytes * (uint32_t)kc4);
 					__syncwarp();
-					if (lane < kc)
-						tma_bulk_g2s(sV + ((size_t)st * MM_K + lane) * MM_LDV, m.values + (int64_t)row * m.value_stride + d0, row_bytes, &full_bar[st]);
+					if (lane < kc4)
+						tma_bulk_g2s_hint(sV + ((size_t)st * MM_K + lane) * MM_LDV, m.values + (int64_t)row * m.value_stride + d0, row_bytes, &full_bar[st], keep);
 				} else if (lane == 0) {
 					mbar_arrive(&full_bar[st]);
 				}
@@ -190,8 +254,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	uint32_t g = 0, it = 0;
 	double acc[4][4][2];  // [query block mi][component block ni][2]
 	for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-		const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off);
+		const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
 		const int ib = it & 1;
+		const int32_t K = ig.K;
+		const int n_stages = (K + MM_K - 1) / MM_K;
 		const int n_steps = ig.n_dc * n_stages;
 		const int n_mi = min(4, (ig.nq - wq * 32 + 7) >> 3);  // 8-query blocks beyond the tile's last query hold only padding
 		for (int s = 0; s < n_steps; s++, g++) {
@@ -204,8 +270,8 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 					for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 			}
 			mbar_wait(&full_bar[st], (g / MM_NS) & 1u);
-			const int kc = min(MM_K, K - c * MM_K);  // multiple of 4 (K is)
-			const double *w_base = sW + (size_t)st * MM_K * MM_LDW + wq * 32 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr]
+			const int kc = (min(MM_K, K - c * MM_K) + 3) & ~3;  // padded to whole MMA k-steps with zero weights
+			const double *w_base = sW + (size_t)(ONE ? ib : st) * MM_K * MM_LDW + wq * 32 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr]
 			const double *v_base = sV + (size_t)st * MM_K * MM_LDV + wd * 32 + fr;  // B[fc][fr] = V[k0 + fc][d0 + fr]
 			if (n_mi > 0) {
 #pragma unroll 2
@@ -253,24 +319,33 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 }
 
 namespace {
-size_t mma_smem_bytes(int N, int F, int lowk)
+size_t mma_smem_bytes(int N, int F, int lowk, bool one)
 {
-	return (size_t)(MM_NS * MM_K * MM_LDV + MM_NS * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64;
+	const int ns = one ? MM_NS_ONE : MM_NS_MULTI, nw = one ? 2 : MM_NS_MULTI;
+	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64;
 }
-template <int NT, bool CUBIC, bool EXACT>
-void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, cudaStream_t st)
+template <int NT, bool CUBIC, bool EXACT, bool ONE>
+void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, cudaStream_t st)
 {
-	auto kern = mesh_tensor_mma_kernel<NT, CUBIC, EXACT>;
+	auto kern = mesh_tensor_mma_kernel<NT, CUBIC, EXACT, ONE>;
 	constexpr int LOWD = NT < (CUBIC ? 2 : 4) ? NT : (CUBIC ? 2 : 4);
-	const size_t smem = mma_smem_bytes(NT, CUBIC ? 4 : 2, 1 << ((CUBIC ? 2 : 1) * LOWD));
+	const size_t smem = mma_smem_bytes(NT, CUBIC ? 4 : 2, 1 << ((CUBIC ? 2 : 1) * LOWD), ONE);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	LOCO_KERNEL("mesh_tensor_mma", st);
 	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, out, out_stride, n_dchunks, dg);
 }
+template <int NT, bool CUBIC, bool EXACT>
+void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, cudaStream_t st)
+{
+	// K = F^NT <= 16 rows (one stage per chunk) only for small NT; the test is a compile-time constant per instantiation
+	constexpr int KT = 1 << ((CUBIC ? 2 : 1) * NT);
+	if constexpr (KT <= MM_K) run_mma1<NT, CUBIC, EXACT, true>(m, w, out, out_stride, n_dchunks, dg, grid, st);
+	else run_mma1<NT, CUBIC, EXACT, false>(m, w, out, out_stride, n_dchunks, dg, grid, st);
+}
 } // namespace
 
 int mesh_mma_tile_queries() { return MM_Q; }
-bool mesh_mma_supported(const DeviceModel &m) { return m.tensor_F > 0 && m.N >= 1 && m.N <= kMaxTemplateN && (m.tensor_K % 4) == 0; }
+bool mesh_mma_supported(const DeviceModel &m) { return m.tensor_F > 0 && m.N >= 1 && m.N <= kMaxTemplateN; }
 
 // queries must already be sorted by leaf with tiles of mesh_mma_tile_queries() (launch_sort_by_leaf)
 int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, cudaStream_t st)
@@ -281,8 +356,9 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	// CTAs share at a time (rows x dg*128 components) stays well inside the L2
 	const int n_stages = (m.tensor_K + MM_K - 1) / MM_K;
 	int dg = std::max(4, (32 + n_stages - 1) / n_stages);
-	const int64_t slice_cap = ((int64_t)48 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
+	const int64_t slice_cap = ((int64_t)28 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
 	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
+	if (const char *e = getenv("LOCO_MESH_DG")) dg = std::max(1, std::min(atoi(e), n_dchunks));  // tuning experiments
 	const int grid = sm_count * 2;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \

@@ -39,4 +39,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same with an L2 eviction-priority hint (createpolicy): value rows that every CTA re-reads are kept with evict_last
+// while the result stream passes through the L2 with evict_first stores
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+// 128-bit store that tells the L2 the line will not be read again
+__device__ __forceinline__ void st_stream_f64x2(double *p, double a, double b, uint64_t policy)
+{
+	asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+	             "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 } // namespace loco

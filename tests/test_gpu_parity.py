@@ -239,3 +239,26 @@ def test_locate_grid_equals_descent_bootstrap(N, basis, level):
     _, leaf1, status1 = m.eval(q)
     assert np.array_equal(leaf0, leaf1) and np.array_equal(status0, status1)
     assert leaf1.max() == m.L - 1
+
+
+@pytest.mark.parametrize("N,level", [(2, 1), (3, 2), (4, 1)])
+def test_mesh_valued_shared_border_rows(N, level):
+    """Cubic grids built with evalCorners=false: border samples share the value object of their clamped in-domain
+    sample (LCAdaptiveGrid.cpp:345-355), which the fp64-MMA mesh kernel exploits by folding equal rows.  A D-component
+    function must equal D scalar functions on the same tree, on every mesh path."""
+    D = 4
+    fns = [lambda p, j=j: float(np.sin(3 * p * (j + 1) + j).sum() + j) for j in range(D)]
+    mesh = capi.Model.bootstrap(N, capi.CUBIC, level, D, False, fn=lambda p: np.array([f(p) for f in fns]), device=0)
+    assert mesh.info["n_value_rows"] - mesh.L < mesh.info["n_samples"]  # rows are shared (centre values add L rows)
+    q = np.random.default_rng(8).random((5000, N)) * 1.000002 - 0.000001
+    outs = {}
+    for simt, path in ((0, 0), (1, 0), (0, 1)):  # folded MMA tiles, DFMA tiles, generic weights + gather
+        mesh.set_option("mesh_simt", simt)
+        mesh.set_option("path", path)
+        outs[(simt, path)], leaf, status = mesh.eval(q)
+    for j in range(D):
+        scalar = capi.Model.bootstrap(N, capi.CUBIC, level, 1, False, fn=fns[j], device=0)
+        ref, leaf_s, status_s = scalar.eval(q)
+        assert np.array_equal(leaf, leaf_s) and np.array_equal(status, status_s)
+        for key, out in outs.items():
+            assert np.abs(out[:, j] - ref).max() <= 1e-12 * (np.abs(ref).max() + 1), key
