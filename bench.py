@@ -212,7 +212,12 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = None
+        try:  # the result gather runs beside the next batch's kernels: give NCCL's stream priority over them
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     if local == 0:
         product_build.build()
     if world > 1:
@@ -284,9 +289,16 @@ def measure(name, w, args, rank, world, local, config, full):
             m.error_check_generated_device(ppl, 1000 + i, d_amp.data_ptr(), d_phase.data_ptr(), 10, 0.05, err.data_ptr(), split.data_ptr(), stream)
     elif D == 1:
         outs = [torch.empty(Q, dtype=torch.float64, device="cuda") for _ in range(2)]
+        # with several GPUs the step is issued in sub-batches so that the gather of a finished part overlaps the rest
+        n_sub = 4 if world > 1 and Q % 4 == 0 and Q >= (1 << 22) else 1
+        Qs = Q // n_sub
 
-        def step(i):
-            m.eval_device(q.data_ptr(), Q, outs[i % 2].data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
+        def step(i, gather=None):
+            for j in range(n_sub):
+                m.eval_device(q.data_ptr() + j * Qs * N * 8, Qs, outs[i % 2].data_ptr() + j * Qs * 8, leaf.data_ptr() + j * Qs * 4,
+                              status.data_ptr() + j * Qs, stream)
+                if gather is not None:
+                    gather(i, j)
     else:
         # mesh-valued: the whole batch of results stays in HBM ([Q x D] doubles; sized for the 180 GB part)
         assert D % 2 == 0, "bench assumes an even value dimension"
@@ -297,14 +309,17 @@ def measure(name, w, args, rank, world, local, config, full):
 
     gathered, handles = None, []
     if world > 1 and D == 1 and name != "c5":
-        gathered = [torch.empty(world * Q, dtype=torch.float64, device="cuda") for _ in range(2)]
-    err_all = None
+        gathered = [torch.empty((n_sub, world, Qs), dtype=torch.float64, device="cuda") for _ in range(2)]  # [sub-batch][rank][query]
+
+    def gather_part(i, j):  # the path's one exchange step: gather the per-shard results, asynchronously on NCCL's stream
+        handles.append(dist.all_gather_into_tensor(gathered[i % 2][j], outs[i % 2][j * Qs:(j + 1) * Qs], async_op=True))
 
     def run(i):
-        step(i)
-        if gathered is not None:  # the path's one exchange step: gather the per-shard results (overlaps the next step)
-            handles.append(dist.all_gather_into_tensor(gathered[i % 2], outs[i % 2], async_op=True))
-        elif world > 1 and name == "c5":  # error maxima: all_reduce(MAX) of the bit patterns + split flags (shard.py)
+        if gathered is not None:
+            step(i, gather_part)
+        else:
+            step(i)
+        if gathered is None and world > 1 and name == "c5":  # error maxima: all_reduce(MAX) of the bit patterns + split flags (shard.py)
             from locointerpolate_b200 import shard
             shard.reduce_error_maxima(err, split)
 

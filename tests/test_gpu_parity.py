@@ -262,3 +262,26 @@ def test_mesh_valued_shared_border_rows(N, level):
         assert np.array_equal(leaf, leaf_s) and np.array_equal(status, status_s)
         for key, out in outs.items():
             assert np.abs(out[:, j] - ref).max() <= 1e-12 * (np.abs(ref).max() + 1), key
+
+
+def test_mesh_valued_proto_file(golden, tmp_path):
+    """A mesh-valued function stored in the reference's own schema (ShapeInfo.tetMesh.vertices) loads and evaluates."""
+    pb, z = golden("cub2d_adapt6")
+    g = protoschema.read_binary(pb)
+    V = 7
+    rng = np.random.default_rng(12)
+    g.D = 3 * V
+    g.sample_value = rng.standard_normal((len(g.sample_center), 3 * V))
+    g.cell_center_value = rng.standard_normal((len(g.cell_split_dir), 3 * V))
+    g.border_center_value = rng.standard_normal((len(g.border_ranges), 3 * V))
+    g.cell_sample_value = g.border_sample_value = None
+    src = str(tmp_path / "mesh.pb")
+    protoschema.write_binary(g, src)
+    m = capi.Model.from_proto(src, device=0)
+    orc = oracleapi.Oracle(protoschema.read_binary(src))
+    q = z["q"][:600]
+    out, leaf, status = m.eval(q)
+    o_out, o_leaf, o_status, scale = orc.eval(q)
+    assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
+    ok = status == 0
+    assert_values_close(out[ok], o_out[ok], scale[ok])

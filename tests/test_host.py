@@ -192,3 +192,33 @@ def test_graph_argument_validation():
     with pytest.raises(capi.LocoError) as e:
         capi.Model.from_graph(g, device=capi.HOST_ONLY)
     assert "could not map the sample from id" in e.value.msg
+
+
+def test_mesh_valued_proto_round_trip(golden, tmp_path):
+    """Mesh values travel in ShapeInfo.tetMesh.vertices (PrecomputedParametricShape.proto:87-99; the slot the public
+    reference no longer reads, LCProtoConverter.cpp:211-263): D = 3 * #vertices doubles per value.  A file written by
+    google.protobuf must load, and what the product writes must parse back into the same values."""
+    pb, _ = golden("cub2d_boot1_adapt")
+    g = protoschema.read_binary(pb)
+    V = 5
+    rng = np.random.default_rng(4)
+    g.D = 3 * V
+    g.sample_value = rng.standard_normal((len(g.sample_center), 3 * V))
+    g.cell_center_value = rng.standard_normal((len(g.cell_split_dir), 3 * V))
+    g.border_center_value = rng.standard_normal((len(g.border_ranges), 3 * V))
+    g.cell_sample_value = g.border_sample_value = None
+    src = str(tmp_path / "mesh.pb")
+    protoschema.write_binary(g, src)
+    m = capi.Model.from_proto(src, device=capi.HOST_ONLY)
+    assert m.D == 3 * V and m.info["n_samples"] == len(g.sample_center)
+    out = str(tmp_path / "mesh_rt.pb")
+    m.save_proto(out)
+    g2 = protoschema.read_binary(out)
+    assert g2.D == 3 * V
+    assert np.array_equal(g2.sample_value, g.sample_value)
+    leaves = np.asarray(g.cell_split_dir) < 0
+    assert np.array_equal(np.asarray(g2.cell_center_value)[leaves], g.cell_center_value[leaves])
+    txt = str(tmp_path / "mesh.txt")
+    m.save_proto(txt, ascii=True)
+    g3 = protoschema.read_text(txt)
+    assert np.array_equal(g3.sample_value, g.sample_value)
