@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="4-D linear mesh-valued (10k vertices, D=30,000), bootstrap 3 (4,096 leaves, K=16); 10M queries streamed in 262,144-query batches (63 GB of results per batch)"),
     "c4": dict(N=6, basis=1, level=1, D=150_000, corners=False, Q=16_384,
                desc="6-D cubic mesh-valued (50k vertices, D=150,000), bootstrap 1 (64 leaves, K=4,096); 10M queries streamed in 16,384-query batches (19.7 GB of results per batch)"),
+    "c4b": dict(N=6, basis=1, level=2, D=150_000, corners=False, Q=262_144, ring=16_384,
+                desc="6-D cubic mesh-valued (50k vertices, D=150,000), bootstrap 2 (4,096 leaves at depth 12, 15,625 value rows = 18.75 GB, K=4,096); "
+                     "262,144 queries per step sorted once and streamed through a 16,384-query ring (19.7 GB) with a per-query checksum"),
     "c5": dict(N=8, basis=0, level=1, D=1, corners=True, Q=64_000_000,
                desc="8-D linear scalar error check, bootstrap 1 (256 leaves, K=256); 1B candidate points per pass in 64M-point batches"),
 }
@@ -196,7 +199,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[args.workload]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c4b": 2, "c5": 100_000}[args.workload]
         base, dt = cpu_reference_arm(w, args.cpu_sample or cpu_default, max(args.steps, 1), args.warmup, args.workload)
         print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": "queries/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -299,6 +302,13 @@ def measure(name, w, args, rank, world, local, config, full):
                               status.data_ptr() + j * Qs, stream)
                 if gather is not None:
                     gather(i, j)
+    elif w.get("ring"):
+        # mesh-valued, streamed: results pass through a ring in leaf order and are reduced to one checksum per query
+        ring = torch.empty((w["ring"], D), dtype=torch.float64, device="cuda")
+        chk = torch.empty(Q, dtype=torch.float64, device="cuda")
+
+        def step(i):
+            m.eval_ring_device(q.data_ptr(), Q, ring.data_ptr(), w["ring"], chk.data_ptr(), leaf.data_ptr(), status.data_ptr(), stream)
     else:
         # mesh-valued: the whole batch of results stays in HBM ([Q x D] doubles; sized for the 180 GB part)
         assert D % 2 == 0, "bench assumes an even value dimension"
@@ -450,7 +460,7 @@ def measure(name, w, args, rank, world, local, config, full):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c5": 100_000}[name]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c4b": 2, "c5": 100_000}[name]
         try:
             cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, name)
         except SystemExit as e:

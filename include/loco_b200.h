@@ -167,8 +167,10 @@ int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t n_queries, 
                            uint8_t *status, void *cuda_stream);
 
 /* mesh-valued batches too large to keep: evaluate but store only a per-query checksum
- * sum_j out[q][j] * (1 + (j % 7))   -> checksum [Q]; `ring` is a device scratch of ring_queries*D doubles
- * that the results are streamed through (every output element is written to HBM exactly once). */
+ *   sum_j out[q][j] * (1 + (j % 7))   -> checksum [Q] (NaN where status != 0); `ring` is a device scratch of
+ * ring_queries * (D rounded up to even) doubles that the results are streamed through.  The WHOLE batch is sorted by
+ * leaf once and then evaluated in ring-sized runs of full leaf tiles, so the ring holds results in leaf order; the call
+ * synchronises the stream once (to split the sorted batch into runs). */
 int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t n_queries, double *ring, int64_t ring_queries,
                                 double *checksum, int32_t *leaf, uint8_t *status, void *cuda_stream);
 

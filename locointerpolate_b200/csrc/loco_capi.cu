@@ -324,7 +324,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const SortWork sw = carve_sort_work(dm, Q, w.misc);
 		if (mesh_mma_supported(dm) && !m->opt_mesh_simt) {
 			m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_mma_tile_queries(), nullptr, st);
-			m->launches += launch_mesh_tensor_mma(dm, sw, Q, out, out_stride, m->sm_count, st);
+			m->launches += launch_mesh_tensor_mma(dm, sw, Q, out, out_stride, m->sm_count, 0, -1, -1, st);
 			m->launches += launch_mesh_nan_rows(dm, status, Q, out, out_stride, st);
 		} else {
 			m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_tile_queries(), nullptr, st);
@@ -579,8 +579,10 @@ int loco_eval_batch(loco_model_t *m, const double *q, int64_t Q, double *out, in
 	NEED_DEVICE(m);
 	CUDA_OK(m, cudaSetDevice(m->device));
 	const DeviceModel &dm = m->dm;
-	// chunk so that one slot's output stays <= 128 MB; three slots overlap H2D, kernels and D2H
-	int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)4 << 20, ((int64_t)128 << 20) / ((int64_t)dm.D * 8)));
+	// three slots overlap H2D, kernels and D2H; a slot's output is 128 MB for scalar functions
+	// mesh-valued: 1 GB of results per slot, so that a chunk still holds enough queries per leaf for the tile kernels
+	const int64_t slot_bytes = dm.D == 1 ? ((int64_t)128 << 20) : ((int64_t)1 << 30);
+	int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)4 << 20, slot_bytes / ((int64_t)dm.D * 8)));
 	chunk = std::min(chunk, std::max<int64_t>(Q, 1));
 	int rc;
 	int slot = 0;
@@ -611,6 +613,45 @@ int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t Q, dou
 	const DeviceModel &dm = m->dm;
 	cudaStream_t st = (cudaStream_t)cuda_stream;
 	int rc;
+	if (dm.D > 1 && mesh_mma_supported(dm) && !m->opt_mesh_simt && m->opt_path != 1 && m->opt_path != 3 && Q > 0 && ring_queries >= mesh_mma_tile_queries()) {
+		// Sort the WHOLE batch by leaf once, then walk the sorted tiles in ring-sized runs: every run is made of full
+		// 64-query tiles of one leaf each (however few queries a ring holds), results sit in the ring in leaf order and the
+		// consumer (here: the checksum) maps them back to query indices through the sorted records.
+		Workspace &w = m->ws[0];
+		if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+		if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+		if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
+		const SortWork sw = carve_sort_work(dm, Q, w.misc);
+		const int TQ = mesh_mma_tile_queries();
+		m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, TQ, nullptr, st);
+		// bucket and tile offsets to the host (2 * (L+1) ints): the split into runs is host logic
+		std::vector<int32_t> h_off((size_t)dm.L + 1), h_tile((size_t)dm.L + 1);
+		CUDA_OK(m, cudaMemcpyAsync(h_off.data(), sw.offset, h_off.size() * 4, cudaMemcpyDeviceToHost, st));
+		CUDA_OK(m, cudaMemcpyAsync(h_tile.data(), sw.tile_off, h_tile.size() * 4, cudaMemcpyDeviceToHost, st));
+		CUDA_OK(m, cudaStreamSynchronize(st));
+		const int64_t n_tiles = h_tile[(size_t)dm.L];
+		// first sorted position of every tile boundary we may cut at (positions are contiguous in tile order)
+		auto tile_pos = [&](int64_t t) -> int64_t {
+			if (t >= n_tiles) return h_off[(size_t)dm.L];
+			const int32_t l = (int32_t)(std::upper_bound(h_tile.begin(), h_tile.end(), (int32_t)t) - h_tile.begin()) - 1;
+			return (int64_t)h_off[(size_t)l] + (t - h_tile[(size_t)l]) * TQ;
+		};
+		for (int64_t t0 = 0; t0 < n_tiles;) {
+			const int64_t p0 = tile_pos(t0);
+			int64_t lo = t0 + 1, hi = n_tiles;  // largest t1 with tile_pos(t1) - p0 <= ring_queries
+			while (lo < hi) {
+				const int64_t mid = (lo + hi + 1) / 2;
+				if (tile_pos(mid) - p0 <= ring_queries) lo = mid; else hi = mid - 1;
+			}
+			const int64_t t1 = lo, n = tile_pos(t1) - p0;
+			m->launches += launch_mesh_tensor_mma(dm, sw, n, ring, dm.value_stride, m->sm_count, t0, t1 - t0, p0, st);
+			m->launches += launch_checksum_sorted(dm, ring, dm.value_stride, sw, p0, n, checksum, st);
+			t0 = t1;
+		}
+		m->launches += launch_checksum_bad(status, Q, checksum, st);
+		CUDA_OK(m, cudaGetLastError());
+		return LOCO_OK;
+	}
 	for (int64_t o = 0; o < Q; o += ring_queries) {
 		const int64_t n = std::min(ring_queries, Q - o);
 		if ((rc = eval_device(m, m->ws[0], st, false, q + o * dm.N, n, ring, dm.value_stride, leaf ? leaf + o : nullptr, status ? status + o : nullptr))) return rc;

@@ -143,7 +143,11 @@ int launch_mesh_nan_rows(const DeviceModel &m, const uint8_t *status, int64_t Q,
 // fp64 MMA version of the mesh tile kernel (loco_mesh_mma.cu); same sorted input, tiles of mesh_mma_tile_queries()
 int mesh_mma_tile_queries();
 bool mesh_mma_supported(const DeviceModel &m);
-int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, cudaStream_t st);
+int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, int64_t tile0, int64_t n_tiles,
+                           int64_t ring_base, cudaStream_t st);
+// checksum[query index of sorted position p] = sum_j ring[p - p0][j] * (1 + j % 7) for p in [p0, p0 + n); queries with an error status get NaN
+int launch_checksum_sorted(const DeviceModel &m, const double *ring, int64_t ring_stride, const SortWork &w, int64_t p0, int64_t n, double *checksum, cudaStream_t st);
+int launch_checksum_bad(const uint8_t *status, int64_t Q, double *checksum, cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
 

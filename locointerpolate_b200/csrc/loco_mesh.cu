@@ -205,6 +205,44 @@ int launch_mesh_nan_rows(const DeviceModel &m, const uint8_t *status, int64_t Q,
 	return 1;
 }
 
+// ring consumer: per-query checksum of results that sit in LEAF ORDER in a ring (row = sorted position - p0); the query
+// index comes from the sorted record
+__global__ void __launch_bounds__(256) checksum_sorted_kernel(const double *__restrict__ ring, int64_t ring_stride, int32_t D, const double *__restrict__ xs,
+                                                               int32_t rs, int64_t p0, double *__restrict__ checksum)
+{
+	__shared__ double red[8];
+	const double *o = ring + (int64_t)blockIdx.x * ring_stride;
+	double acc = 0.0;
+	for (int j = threadIdx.x; j < D; j += blockDim.x) acc += o[j] * (double)(1 + j % 7);
+	for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+		const int32_t qi = (int32_t)__double_as_longlong(xs[(p0 + blockIdx.x) * rs + rs - 1]);
+		checksum[qi] = s;
+	}
+}
+__global__ void checksum_bad_kernel(const uint8_t *__restrict__ status, int64_t Q, double *__restrict__ checksum)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < Q && status[i] != ST_OK) checksum[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+int launch_checksum_sorted(const DeviceModel &m, const double *ring, int64_t ring_stride, const SortWork &w, int64_t p0, int64_t n, double *checksum, cudaStream_t st)
+{
+	if (n <= 0) return 0;
+	LOCO_KERNEL("checksum", st);
+	checksum_sorted_kernel<<<(unsigned)n, 256, 0, st>>>(ring, ring_stride, m.D, w.xs, sorted_row_doubles(m.N), p0, checksum);
+	return 1;
+}
+int launch_checksum_bad(const uint8_t *status, int64_t Q, double *checksum, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	checksum_bad_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(status, Q, checksum);
+	return 1;
+}
+
 size_t mesh_tiles_smem_bytes(int N, int F)
 {
 	return (size_t)(2 * MT_K * MT_D + 2 * MT_K * MT_Q + N * F * MT_Q) * sizeof(double) + MT_Q * sizeof(int32_t) + 64;

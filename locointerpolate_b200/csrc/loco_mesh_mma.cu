@@ -53,11 +53,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 
 struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc, row0, K; };  // row0, K: the leaf's folded row list in DeviceModel::fold_row
 // item -> (chunk group, tile) -> leaf and query range; identical arithmetic in the producer and in every consumer warp
-__device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t n_tiles, int32_t L, int32_t n_dchunks, int dg, const int32_t *__restrict__ offset,
+__device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, int64_t n_tiles, int32_t L, int32_t n_dchunks, int dg, const int32_t *__restrict__ offset,
                                                   const int32_t *__restrict__ tile_off, const int32_t *__restrict__ fold_off)
 {
 	ItemGeom g;
-	const int64_t dgroup = item / n_tiles, tile = item - dgroup * n_tiles;
+	const int64_t dgroup = item / n_tiles, tile = tile0 + (item - dgroup * n_tiles);
 	int32_t lo = 0, hi = L;  // last leaf whose first tile is <= tile
 	while (lo < hi) {
 		const int32_t mid = (lo + hi) >> 1;
@@ -77,7 +77,8 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t n_tiles,
 template <int NT, bool CUBIC, bool EXACT, bool ONE>
 __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceModel m, const double *__restrict__ xs, const int32_t *__restrict__ offset,
                                                                          const int32_t *__restrict__ tile_off, double *__restrict__ out,
-                                                                         int64_t out_stride, int32_t n_dchunks, int32_t dg)
+                                                                         int64_t out_stride, int32_t n_dchunks, int32_t dg, int64_t tile0, int64_t n_tiles_arg,
+                                                                         int64_t ring_base)
 {
 	constexpr int F = CUBIC ? 4 : 2;
 	constexpr int LOGF = CUBIC ? 2 : 1;
@@ -101,8 +102,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	}
 	__syncthreads();
 
+	// tiles [tile0, tile0 + n_tiles) of the sorted batch; ring_base >= 0: results go to row (sorted position - ring_base) of
+	// `out` (a ring the caller consumes in leaf order) instead of row (query index)
 	const int32_t L = m.L;
-	const int64_t n_tiles = tile_off[L];
+	const int64_t n_tiles = n_tiles_arg >= 0 ? n_tiles_arg : (int64_t)tile_off[L];
 	const int32_t n_dgroups = (n_dchunks + dg - 1) / dg;
 	const int64_t total = n_tiles * n_dgroups;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 		uint32_t g = 0;   // running step counter: stage = g % MM_NS, use count = g / MM_NS
 		uint32_t it = 0;  // running item counter: item buffer = it & 1
 		for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-			const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
+			const ItemGeom ig = item_geometry(item, tile0, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
 			const int ib = it & 1;
 			// the consumers are done with this item buffer (two items ago); a fresh barrier passes the parity-1 wait
 			mbar_wait(&item_bar[ib], ((it >> 1) & 1u) ^ 1u);
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	uint32_t g = 0, it = 0;
 	double acc[4][4][2];  // [query block mi][component block ni][2]
 	for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-		const ItemGeom ig = item_geometry(item, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
+		const ItemGeom ig = item_geometry(item, tile0, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
 		const int ib = it & 1;
 		const int32_t K = ig.K;
 		const int n_stages = (K + MM_K - 1) / MM_K;
@@ -299,7 +302,8 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				for (int mi = 0; mi < 4; mi++) {
 					const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
 					if (qi < 0) continue;
-					double *o = out + (int64_t)qi * out_stride + d0;
+					const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
+					double *o = out + orow * out_stride + d0;
 #pragma unroll
 					for (int ni = 0; ni < 4; ni++) {
 						const int col = wd * 32 + ni * 8 + 2 * fc;
@@ -325,22 +329,24 @@ size_t mma_smem_bytes(int N, int F, int lowk, bool one)
 	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64;
 }
 template <int NT, bool CUBIC, bool EXACT, bool ONE>
-void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, cudaStream_t st)
+void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, int64_t tile0, int64_t n_tiles,
+              int64_t ring_base, cudaStream_t st)
 {
 	auto kern = mesh_tensor_mma_kernel<NT, CUBIC, EXACT, ONE>;
 	constexpr int LOWD = NT < (CUBIC ? 2 : 4) ? NT : (CUBIC ? 2 : 4);
 	const size_t smem = mma_smem_bytes(NT, CUBIC ? 4 : 2, 1 << ((CUBIC ? 2 : 1) * LOWD), ONE);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	LOCO_KERNEL("mesh_tensor_mma", st);
-	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, out, out_stride, n_dchunks, dg);
+	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, out, out_stride, n_dchunks, dg, tile0, n_tiles, ring_base);
 }
 template <int NT, bool CUBIC, bool EXACT>
-void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, cudaStream_t st)
+void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, int64_t tile0, int64_t n_tiles,
+             int64_t ring_base, cudaStream_t st)
 {
 	// K = F^NT <= 16 rows (one stage per chunk) only for small NT; the test is a compile-time constant per instantiation
 	constexpr int KT = 1 << ((CUBIC ? 2 : 1) * NT);
-	if constexpr (KT <= MM_K) run_mma1<NT, CUBIC, EXACT, true>(m, w, out, out_stride, n_dchunks, dg, grid, st);
-	else run_mma1<NT, CUBIC, EXACT, false>(m, w, out, out_stride, n_dchunks, dg, grid, st);
+	if constexpr (KT <= MM_K) run_mma1<NT, CUBIC, EXACT, true>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st);
+	else run_mma1<NT, CUBIC, EXACT, false>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st);
 }
 } // namespace
 
@@ -348,9 +354,13 @@ int mesh_mma_tile_queries() { return MM_Q; }
 bool mesh_mma_supported(const DeviceModel &m) { return m.tensor_F > 0 && m.N >= 1 && m.N <= kMaxTemplateN; }
 
 // queries must already be sorted by leaf with tiles of mesh_mma_tile_queries() (launch_sort_by_leaf)
-int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, cudaStream_t st)
+// tile0 / n_tiles: the range of sorted tiles to evaluate (n_tiles < 0: all of them, read from the device);
+// ring_base >= 0: write row (sorted position - ring_base) instead of row (query index)
+int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, double *out, int64_t out_stride, int sm_count, int64_t tile0, int64_t n_tiles,
+                           int64_t ring_base, cudaStream_t st)
 {
-	if (Q <= 0) return 0;
+	if (Q <= 0 || n_tiles == 0) return 0;
+	if (n_tiles < 0) tile0 = 0;  // the kernel reads the tile count from the device (no host synchronisation)
 	const int n_dchunks = (m.D + MM_D - 1) / MM_D;
 	// chunks per item: enough steps per item to amortise the per-item tables, while the slice of the value table all
 	// CTAs share at a time (rows x dg*128 components) stays well inside the L2
@@ -363,8 +373,8 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \
 	case NT:                                                                                                            \
-		if (cubic) { if (exact) run_mma<NT, true, true>(m, w, out, out_stride, n_dchunks, dg, grid, st); else run_mma<NT, true, false>(m, w, out, out_stride, n_dchunks, dg, grid, st); } \
-		else { if (exact) run_mma<NT, false, true>(m, w, out, out_stride, n_dchunks, dg, grid, st); else run_mma<NT, false, false>(m, w, out, out_stride, n_dchunks, dg, grid, st); }     \
+		if (cubic) { if (exact) run_mma<NT, true, true>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st); else run_mma<NT, true, false>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st); } \
+		else { if (exact) run_mma<NT, false, true>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st); else run_mma<NT, false, false>(m, w, out, out_stride, n_dchunks, dg, grid, tile0, n_tiles, ring_base, st); }     \
 		break;
 	switch (m.N) { LOCO_MCASE(1) LOCO_MCASE(2) LOCO_MCASE(3) LOCO_MCASE(4) LOCO_MCASE(5) LOCO_MCASE(6) LOCO_MCASE(7) LOCO_MCASE(8) default: return 0; }
 #undef LOCO_MCASE
