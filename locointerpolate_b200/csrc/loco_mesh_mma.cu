@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				return ln < kc4 ? __ldg(rows + min(c * MM_K + ln, K - 1)) : 0;
 			};
 			int32_t my_row = row_of(0, lane);
+			int low = 0, hd[NT > LOWD ? NT - LOWD : 1];
+			double ph = 1.0;
 			if (ONE) {
 				// all rows fit one stage: the weights do not depend on the chunk, write them once per item (item buffer ib;
 				// the first stage barrier of the item publishes them)
@@ -199,17 +201,20 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				// ---- weights of the stage: w[kk] = low[k % lowK] * high(k / lowK), k = c*MM_K + kk, walked incrementally
 				double wreg[ONE ? 1 : MM_K];
 				if (!ONE) {
-					int low = (c * MM_K) % lowK, high = (c * MM_K) / lowK;
-					int hd[NT > LOWD ? NT - LOWD : 1];
-#pragma unroll
-					for (int d = LOWD; d < NT; d++) { hd[d - LOWD] = high % nd[d]; high /= nd[d]; }
+					// the mixed-radix position (low, hd[]) of row k is carried from stage to stage (no divisions): a chunk
+					// starts at row 0, and every full stage advances it by exactly MM_K rows
 					auto high_product = [&]() {
 						double p = 1.0;
 #pragma unroll
 						for (int d = LOWD; d < NT; d++) p *= sF[(d * F + hd[d - LOWD]) * MM_Q + q];
 						return p;
 					};
-					double ph = high_product();
+					if (c == 0) {
+						low = 0;
+#pragma unroll
+						for (int d = LOWD; d < NT; d++) hd[d - LOWD] = 0;
+						ph = high_product();
+					}
 #pragma unroll
 					for (int kk = 0; kk < MM_K; kk++) {
 						wreg[kk] = kk < kc ? sL[low * MM_Q + q] * ph : 0.0;
