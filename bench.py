@@ -119,7 +119,11 @@ def build_model(capi, w, device):
 
 
 def cpu_reference_arm(w, sample_q, steps, warmup, name):
-    """The reference's own CPU implementation on the host cores (oracle/_ref when present, else the oracle port)."""
+    """The reference's own CPU implementation on the host cores (oracle/_ref when present, else the oracle port).
+    Mesh-valued workloads: the reference has no mesh value type (LCFunctionValue.cpp:20-31), so a query costs the
+    reference's own locate + influencing-set assembly + weights, then `val += w * other` over the D components
+    (SURVEY.md 8d); to bound host memory the table has min(D, 3000) columns and the rate is scaled by D_used / D
+    (the component loop is linear in D and dominates)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from locointerpolate_b200 import capi
     from oracle import oracleapi, refapi
@@ -127,46 +131,40 @@ def cpu_reference_arm(w, sample_q, steps, warmup, name):
     import tempfile
     cores = len(os.sched_getaffinity(0))
     N, D = w["N"], w["D"]
-    wl = dict(w)
-    if D > 1:
-        # the reference has no mesh-valued implementation (LCFunctionValue.cpp:20-31): CPU side = reference weights +
-        # a plain r[j] += w*v[j] loop; the port does exactly that, on a reduced D to bound memory
-        wl["D"] = min(D, 3000)
-    m, _, _ = build_model(capi, {**wl, "D": 1} if D == 1 else wl, capi.HOST_ONLY)
-    kind = "port"
+    m, _, _ = build_model(capi, {**w, "D": 1}, capi.HOST_ONLY)  # the same tree with scalar values
+    tmp = tempfile.mktemp(suffix=".pb")
+    m.save_proto(tmp)
+    g = protoschema.read_binary(tmp)
+    os.unlink(tmp)
     rng = np.random.default_rng(99)
     q = rng.random((sample_q, N))
-    if D == 1 and refapi.available():
-        tmp = tempfile.mktemp(suffix=".pb")
-        m.save_proto(tmp)
-        g = protoschema.read_binary(tmp)
-        os.unlink(tmp)
+    scale, note = 1.0, ""
+    if refapi.available():
         fn = refapi.RefFn.from_graph(g)
-        kind = "reference"
-        run = lambda: fn.eval_fork(q, cores)
-        used = cores
-    else:
+        kind, used = "reference", cores
         if D == 1:
-            tmp = tempfile.mktemp(suffix=".pb")
-            m.save_proto(tmp)
-            g = protoschema.read_binary(tmp)
-            os.unlink(tmp)
+            run = lambda: fn.eval_fork(q, cores)
         else:
-            g = None
-        if g is None:
-            raise SystemExit("mesh-valued CPU baseline needs a host value table; use --workload c1/c2/c5 for --impl reference")
+            Du = min(D, 3000)
+            table = rng.standard_normal((fn.S, Du))
+            scale = Du / D
+            note = f"; mesh values: reference weights + component loop over {Du} of {D} columns, rate scaled by {Du}/{D}"
+            run = lambda: fn.eval_mesh_fork(q, table, cores)
+    else:
+        if D != 1:
+            raise SystemExit("mesh-valued CPU baseline needs oracle/_ref/liblocoref.so")
         orc = oracleapi.Oracle(g)
+        kind, used = "port", 1
         run = lambda: orc.eval(q)
-        used = 1
     for _ in range(warmup):
         run()
     t0 = time.perf_counter()
     for _ in range(steps):
         run()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=sample_q / dt, unit="queries/s", cores=used, kind=kind,
-                sample=f"{sample_q} uniform queries of workload {name} per step, {steps} steps, fork-parallel over {used} host cores"
-                if kind == "reference" else f"{sample_q} uniform queries of workload {name} per step, single thread"), dt
+    how = f"fork-parallel over {used} host cores" if kind == "reference" else "single thread"
+    return dict(value=sample_q / dt * scale, unit="queries/s", cores=used, kind=kind,
+                sample=f"{sample_q} uniform queries of workload {name} per step, {steps} steps, {how}{note}"), dt
 
 
 def main():
@@ -199,7 +197,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c4b": 2, "c5": 100_000}[args.workload]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000}[args.workload]
         base, dt = cpu_reference_arm(w, args.cpu_sample or cpu_default, max(args.steps, 1), args.warmup, args.workload)
         print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": "queries/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -460,7 +458,7 @@ def measure(name, w, args, rank, world, local, config, full):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 200, "c4": 2, "c4b": 2, "c5": 100_000}[name]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000}[name]
         try:
             cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, name)
         except SystemExit as e:

@@ -523,6 +523,61 @@ int ref_fn_weights(void *fp, int leafIdx, const double *cube, int *ids, double *
 	return k;
 }
 
+// Mesh-valued CPU baseline: the reference has no mesh-valued LCFunctionValue (LCFunctionValue.cpp:20-31), so a
+// query costs the reference's own locate + influencing-set assembly + weights (getAllInfluencingSamples,
+// getInterpolationWeight) followed by LCRealFunctionValue::add's `val += weight * other` applied to each of the D
+// components of a row-major table [S x D].  Returns a checksum of the results.
+double ref_fn_eval_mesh_sum(void *fp, const double *q, long Q, const double *table, long D)
+{
+	CoutMute mute;
+	RefFn *r = (RefFn *)fp;
+	int N = r->fn->getNParams();
+	std::vector<double> p(N), res((size_t)D);
+	double acc = 0;
+	for (long i = 0; i < Q; i++) {
+		for (int d = 0; d < N; d++) p[d] = q[i * N + d];
+		std::vector<double> cube = r->fn->mapToStandardHypercube(p);
+		LCAdaptiveGridCell *cell = nullptr;
+		if (!r->fn->getRoot()->getCointainingLeaf(cube, &cell).isOK()) continue;
+		std::vector<std::pair<LCSample *, LCFunctionValue *>> infl;
+		std::vector<LCFunctionValue *> del;
+		if (!cell->getAllInfluencingSamples((LCBasisFunction::LCBasisFunctionType)r->basis, &infl, &del).isOK()) continue;
+		Eigen::VectorXd pos(N);
+		for (int d = 0; d < N; d++) pos(d) = cube[d];
+		std::fill(res.begin(), res.end(), 0.0);
+		for (auto s : infl) {
+			double wt = 0;
+			s.first->getInterpolationWeight(pos, &wt);
+			const double *row = table + (long)r->sampleIndex[s.first] * D;
+			for (long j = 0; j < D; j++) res[(size_t)j] += wt * row[j];
+		}
+		for (auto v : del) delete v;
+		acc += res[0] + res[(size_t)D - 1];
+	}
+	return acc;
+}
+
+int ref_fn_eval_mesh_fork(void *fp, const double *q, long Q, const double *table, long D, int procs)
+{
+	RefFn *r = (RefFn *)fp;
+	int N = r->fn->getNParams();
+	std::vector<pid_t> pids;
+	for (int k = 0; k < procs; k++) {
+		long lo = Q * k / procs, hi = Q * (k + 1) / procs;
+		pid_t pid = fork();
+		if (pid == 0) {
+			volatile double sink = ref_fn_eval_mesh_sum(fp, q + lo * N, hi - lo, table, D);
+			(void)sink;
+			_exit(0);
+		}
+		if (pid < 0) return -1;
+		pids.push_back(pid);
+	}
+	int rc = 0;
+	for (pid_t pid : pids) { int st = 0; waitpid(pid, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) rc = -2; }
+	return rc;
+}
+
 // Sorted sample indices of getAllInfluencingSamples for a leaf; returns K (or -1 if cap too small).
 int ref_fn_support(void *fp, int leafIdx, int *ids, int cap)
 {

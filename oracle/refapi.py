@@ -50,6 +50,9 @@ def lib():
         L.ref_fn_dump_border.argtypes = [vp] * 6
         L.ref_fn_eval.argtypes = [vp, vp, l, vp, vp, vp]
         L.ref_fn_eval_deriv.argtypes = [vp, vp, l, i, vp]
+        L.ref_fn_eval_mesh_sum.restype = d
+        L.ref_fn_eval_mesh_sum.argtypes = [vp, vp, l, vp, l]
+        L.ref_fn_eval_mesh_fork.argtypes = [vp, vp, l, vp, l, i]
         L.ref_fn_eval_sum.restype = d
         L.ref_fn_eval_sum.argtypes = [vp, vp, l]
         L.ref_fn_eval_fork.argtypes = [vp, vp, l, i]
@@ -166,6 +169,15 @@ class RefFn:
         out = np.empty(len(q))
         lib().ref_fn_eval_deriv(self.h, _p(q), len(q), direction, _p(out))
         return out
+
+    def eval_mesh_fork(self, q, table, procs):
+        """mesh-valued CPU baseline: reference weights + `val += w * other` over the D columns of table [S, D]"""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.shape[0] == self.S
+        rc = lib().ref_fn_eval_mesh_fork(self.h, _p(q), len(q), _p(table), table.shape[1], procs)
+        if rc != 0:
+            raise RuntimeError(f"fork-parallel mesh evaluation failed ({rc})")
 
     def eval_sum(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)
