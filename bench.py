@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (c3, c4) reported under other_workloads")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted TMA tiles, 4 L2-resident sorted chunks")
+    ap.add_argument("--overlap", type=int, default=0, help="streams the chunks of the sorted path are dealt over (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="queries per L2-resident chunk of the sorted path (0 = auto)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -268,6 +269,8 @@ def measure(name, w, args, rank, world, local, config, full):
     m, amp, phase = build_model(capi, w, local)
     m.set_option("path", args.path)
     m.set_option("chunk", args.chunk)
+    if args.overlap:
+        m.set_option("overlap", args.overlap)
     info = m.info
     N, D, Q = w["N"], w["D"], w["Q"]
     gen = torch.Generator("cuda").manual_seed(1234 + rank)
@@ -331,6 +334,9 @@ def measure(name, w, args, rank, world, local, config, full):
             from locointerpolate_b200 import shard
             shard.reduce_error_maxima(err, split)
 
+    sampler = ClockSampler(local)
+    if rank == 0 and full:
+        sampler.start()  # from the warm-up on: short timed regions would otherwise fall between two 100 ms samples
     for i in range(warmup):
         if flush is not None:
             flush.zero_()
@@ -342,9 +348,6 @@ def measure(name, w, args, rank, world, local, config, full):
     if world > 1:
         dist.barrier()
     launches0 = m.kernel_launches
-    sampler = ClockSampler(local)
-    if rank == 0 and full:
-        sampler.start()
     t_wall = time.perf_counter()
     if flush is None:
         # inputs + outputs of a step exceed the L2: time the K steps back to back
@@ -385,10 +388,14 @@ def measure(name, w, args, rank, world, local, config, full):
     bad = int((status != 0).sum().item()) if name != "c5" else 0
 
     # ---- every kernel of the step, CUDA events around each launch on the launching stream (no flush, no gather)
+    #      (measured with the chunks of the sorted path on ONE stream: with the default two-stream overlap the events of
+    #      a kernel would also cover the kernels running beside it)
+    m.set_option("overlap", 1)
     m.profile_begin()
     for i in range(steps):
         step(i)
     prof = m.profile_end()
+    m.set_option("overlap", args.overlap or 2)
     tot_ms = sum(v["total_ms"] for v in prof.values()) or 1.0
     kernels = {k: {"launches_per_step": v["launches"] / steps, "ms_per_launch": v["total_ms"] / v["launches"], "share": v["total_ms"] / tot_ms}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}
@@ -397,6 +404,7 @@ def measure(name, w, args, rank, world, local, config, full):
     q_per_launch = Q / kernels[dom]["launches_per_step"]
     T = info["n_terms"] / info["n_leaves"]
     K = info["n_support_entries"] / info["n_leaves"]
+    Kf = info["n_fold_entries"] / info["n_leaves"] if info.get("n_fold_entries") else K
     role = KERNEL_ROLE.get(dom, "all")
     algo_q = role_bytes_per_query(role, N, info["depth"], T, K, D)
     algo = algo_q * q_per_launch
@@ -417,8 +425,11 @@ def measure(name, w, args, rank, world, local, config, full):
                                "achieved_gbs": path_q * Q / (step_kernel_ms * 1e-3) / 1e9},
                 "compulsory": {"bytes_per_step": compulsory, "achieved_gbs": compulsory / (step_kernel_ms * 1e-3) / 1e9,
                                "frac": compulsory / (step_kernel_ms * 1e-3) / 1e9 / peak},
-                "fp64": {"flops_per_query": 2.0 * K * D, "achieved_tflops": 2.0 * K * D * Q / (step_kernel_ms * 1e-3) / 1e12, "peak_tflops": 36.4,
-                         "peak_source": "measured DFMA loop, tools/micro/dmma_rate.cu"} if D > 1 else None,
+                "fp64": {"rows_per_leaf": K, "rows_per_leaf_folded": Kf, "flops_per_query": 2.0 * Kf * D,
+                         "achieved_tflops": 2.0 * Kf * D * Q / (step_kernel_ms * 1e-3) / 1e12, "peak_tflops": 36.4,
+                         "peak_source": "measured DFMA loop, tools/micro/dmma_rate.cu",
+                         "note": "flops counted on the folded rows actually multiplied (samples sharing one value object are summed first)"}
+                if D > 1 else None,
                 "note": "algorithmic bytes = SURVEY.md 8(d): the reference's per-query data flow without caches, restricted to the part the dominant "
                         "kernel covers (kernel_role); leaf data is served from L1/L2/shared memory, so 'achieved' may exceed the HBM peak -- "
                         "'compulsory' is what must cross HBM (queries in, results out, model once)"}

@@ -92,6 +92,7 @@ typedef struct loco_info {
 	int32_t depth, max_support, max_terms, device;
 	int64_t n_samples, n_value_rows, n_leaves, n_cells, n_border_cells, n_basis_functions;
 	int64_t n_support_entries, n_terms, device_bytes;
+	int64_t n_fold_entries;  /* value rows over all tensor leaves after folding samples that share a value object (0: no tensor leaves) */
 } loco_info_t;
 
 /* f : original parameter space [N] -> value [D]   (LCFunction::evalShapeInfo, LCFunction/LCFunction.h:32) */
@@ -215,6 +216,7 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
 /* options: "lut" 1 locate grid before the k-d descent (default) | 0 descent from the root only;
  *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
  *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto);
+ *          "overlap" 1..4 (default 2): internal streams the chunks of path 4 are dealt over (forked from / joined to the caller's);
  *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0) */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */

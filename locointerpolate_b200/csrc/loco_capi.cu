@@ -46,7 +46,8 @@ const int kSlots = 3;  // pipeline depth of the host-buffer path
 struct Workspace {
 	cudaStream_t stream = nullptr;
 	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr, *sorted = nullptr;
-	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0, sorted_b = 0;
+	void *sortedx[3] = {nullptr, nullptr, nullptr};  // workspaces of the additional streams of the sorted path
+	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0, sorted_b = 0, sortedx_b[3] = {0, 0, 0};
 };
 
 } // namespace
@@ -66,9 +67,13 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 2;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
+	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
+	// kernels of one chunk overlap the evaluation of another
+	cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -260,6 +265,11 @@ int build_device_model(loco_model *m)
 	std::vector<double>().swap(f.dterm_w);
 	std::vector<int32_t>().swap(f.dterm_row);
 	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamCreateWithFlags(&m->ws[s].stream, cudaStreamNonBlocking));
+	for (int k = 0; k < 4; k++) {
+		CUDA_OK(m, cudaStreamCreateWithFlags(&m->aux[k], cudaStreamNonBlocking));
+		CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_join[k], cudaEventDisableTiming));
+	}
+	CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
 	return LOCO_OK;
 }
 
@@ -289,17 +299,35 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool tiles = !in_cube && m->opt_path == 2;
 		if (sorted) {
 			// chunks sized so that records (32 B/query) + the out slice stay L2 resident; never fewer than ~16 queries per leaf
-			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 23, (int64_t)dm.L * 16);
+			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 16);
 			chunk = std::min(chunk, Q);
 			int rc;
 			if ((rc = grow(m, &w.sorted, &w.sorted_b, sorted_work_bytes(dm, chunk)))) return rc;
 			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
 			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
-			const SortedWork sw = carve_sorted_work(dm, w.sorted);
-			launch_sorted_reset(dm, sw, st);
-			for (int64_t o = 0; o < Q; o += chunk) {
+			const int64_t n_chunks = (Q + chunk - 1) / chunk;
+			const int ns = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)4, m->opt_overlap, n_chunks}));
+			SortedWork sw[4];
+			cudaStream_t run_on[4] = {st, st, st, st};
+			sw[0] = carve_sorted_work(dm, w.sorted);
+			for (int k = 1; k < ns; k++) {
+				if ((rc = grow(m, &w.sortedx[k - 1], &w.sortedx_b[k - 1], sorted_work_bytes(dm, chunk)))) return rc;
+				sw[k] = carve_sorted_work(dm, w.sortedx[k - 1]);
+			}
+			if (ns > 1) {
+				// fork: the auxiliary streams start after everything already queued on the caller's stream
+				CUDA_OK(m, cudaEventRecord(m->ev_fork, st));
+				for (int k = 0; k < ns; k++) { CUDA_OK(m, cudaStreamWaitEvent(m->aux[k], m->ev_fork, 0)); run_on[k] = m->aux[k]; }
+			}
+			for (int k = 0; k < ns; k++) launch_sorted_reset(dm, sw[k], run_on[k]);
+			int k = 0;
+			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
 				const int64_t n = std::min(chunk, Q - o);
-				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw, m->sm_count, st);
+				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw[k], m->sm_count, run_on[k]);
+			}
+			if (ns > 1) {
+				// join: the caller's stream continues when all of them are done
+				for (int j = 0; j < ns; j++) { CUDA_OK(m, cudaEventRecord(m->ev_join[j], m->aux[j])); CUDA_OK(m, cudaStreamWaitEvent(st, m->ev_join[j], 0)); }
 			}
 		} else if (tiles) {
 			int rc;
@@ -466,9 +494,14 @@ void loco_free(loco_model_t *m)
 	if (!m) return;
 	if (!m->host_only && (!m->allocs.empty() || m->ws[0].stream)) cudaSetDevice(m->device);
 	for (void *p : m->allocs) cudaFree(p);
+	for (int k = 0; k < 4; k++) {
+		if (m->aux[k]) cudaStreamDestroy(m->aux[k]);
+		if (m->ev_join[k]) cudaEventDestroy(m->ev_join[k]);
+	}
+	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
 	for (int s = 0; s < kSlots; s++) {
 		Workspace &w = m->ws[s];
-		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted}) if (p) cudaFree(p);
+		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted, w.sortedx[0], w.sortedx[1], w.sortedx[2]}) if (p) cudaFree(p);
 		if (w.stream) cudaStreamDestroy(w.stream);
 	}
 	delete m;
@@ -487,6 +520,7 @@ int loco_model_info(const loco_model_t *m, loco_info_t *info)
 	info->n_support_entries = f.sup_off.back();
 	info->n_terms = f.term_off.back();
 	info->device_bytes = m->device_bytes;
+	info->n_fold_entries = f.fold_off.empty() ? 0 : f.fold_off.back();
 	return LOCO_OK;
 }
 
@@ -832,6 +866,7 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "path")) { m->opt_path = value; return LOCO_OK; }
 	if (!strcmp(name, "fp32")) { m->opt_fp32 = value; return LOCO_OK; }
 	if (!strcmp(name, "mesh_simt")) { m->opt_mesh_simt = value; return LOCO_OK; }  // 1: DFMA register-tile mesh kernel instead of the fp64 MMA one
+	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
 	if (!strcmp(name, "lut")) {  // 0: plain k-d descent from the root, 1: locate grid first (default)
 		if (m->dm.lut) m->d_lut = m->dm.lut;

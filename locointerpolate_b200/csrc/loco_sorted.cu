@@ -42,24 +42,35 @@ __device__ __forceinline__ void ld_sector_cg(const double *p, double &a, double 
 // ---------------------------------------------------------------------------------------------------
 // 1. locate + histogram
 // ---------------------------------------------------------------------------------------------------
+constexpr int kCountItems = 2;  // queries per thread: two independent load -> locate -> atomic chains in flight
 template <int NT>
 __global__ void __launch_bounds__(256) sorted_count_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
                                                             uint8_t *__restrict__ status_out, double *__restrict__ out, int32_t *count)
 {
 	const int N = NT > 0 ? NT : m.N;
-	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= Q) return;
-	Coord<NT> x;
-	double p[NT > 0 ? NT : kMaxN];
+	const int64_t i0 = (int64_t)blockIdx.x * (256 * kCountItems) + threadIdx.x;
+	double p[kCountItems][NT > 0 ? NT : kMaxN];
 #pragma unroll
-	for (int d = 0; d < N; d++) p[d] = q[i * N + d];
-	map_to_cube<NT>(m, p, x);
-	const int32_t leaf = descend<NT>(m, x);
-	const uint8_t st = located_status<NT>(m, x, leaf);
-	leaf_out[i] = leaf;
-	status_out[i] = st;
-	if (st == ST_OK) atomicAdd(count + leaf, 1);  // result unused: a fire-and-forget RED
-	else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+	for (int k = 0; k < kCountItems; k++) {
+		const int64_t i = i0 + k * 256;
+		if (i < Q) {
+#pragma unroll
+			for (int d = 0; d < N; d++) p[k][d] = q[i * N + d];
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < kCountItems; k++) {
+		const int64_t i = i0 + k * 256;
+		if (i >= Q) continue;
+		Coord<NT> x;
+		map_to_cube<NT>(m, p[k], x);
+		const int32_t leaf = descend<NT>(m, x);
+		const uint8_t st = located_status<NT>(m, x, leaf);
+		leaf_out[i] = leaf;
+		status_out[i] = st;
+		if (st == ST_OK) atomicAdd(count + leaf, 1);  // result unused: a fire-and-forget RED
+		else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+	}
 }
 
 // exclusive scan of the histogram into bucket cursors; clears the histogram for the next chunk.
@@ -228,7 +239,7 @@ template <int NT>
 void run_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, double *out, const SortedWork &w, cudaStream_t st)
 {
 	{ LOCO_KERNEL("sorted_count", st);
-	sorted_count_kernel<NT><<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
+	sorted_count_kernel<NT><<<(unsigned)((Q + 256 * kCountItems - 1) / (256 * kCountItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
 	LOCO_KERNEL("sorted_scan", st);
 	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, m.L);
 }
