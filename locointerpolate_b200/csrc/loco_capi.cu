@@ -67,7 +67,7 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 2;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 2, opt_uniform = 1;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
@@ -206,6 +206,7 @@ int build_device_model(loco_model *m)
 	if (f.tensor_F > 0 && f.N <= kMaxTemplateN) {
 		const int F = f.tensor_F, K = f.tensor_K, N = f.N;
 		dm.tensor_F = F; dm.tensor_K = K;
+		dm.tensor_uniform = (f.tensor_uniform && m->opt_uniform) ? 1 : 0;
 		dm.tl_voff = (N * F + N + 1) & ~1;
 		dm.tl_stride = f.D == 1 ? ((dm.tl_voff + K + 1) & ~1) : dm.tl_voff;
 		std::vector<double> blk((size_t)f.L * dm.tl_stride, 0.0);
@@ -866,6 +867,7 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "path")) { m->opt_path = value; return LOCO_OK; }
 	if (!strcmp(name, "fp32")) { m->opt_fp32 = value; return LOCO_OK; }
 	if (!strcmp(name, "mesh_simt")) { m->opt_mesh_simt = value; return LOCO_OK; }  // 1: DFMA register-tile mesh kernel instead of the fp64 MMA one
+	if (!strcmp(name, "uniform")) { m->opt_uniform = value; m->dm.tensor_uniform = (m->flat.tensor_uniform && value) ? 1 : 0; return LOCO_OK; }  // 0: four separate factor evaluations
 	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
 	if (!strcmp(name, "lut")) {  // 0: plain k-d descent from the root, 1: locate grid first (default)

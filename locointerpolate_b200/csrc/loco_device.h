@@ -39,7 +39,7 @@ struct DeviceModel {
 	const int32_t *dterm_row;
 	// tensor-product leaves (tensor_F > 0): one block of tl_stride doubles per leaf,
 	//   [N*F centres | N supports-or-reciprocals | pad to even | F^N sample values in tensor order (D == 1 only)]
-	int32_t tensor_F, tensor_K, tl_stride, tl_voff;
+	int32_t tensor_F, tensor_K, tl_stride, tl_voff, tensor_uniform;
 	const double *tl_block;           // [L * tl_stride]
 	const int32_t *tl_row;            // [L * F^N] value rows in tensor order
 	// locate grid (Flat::lut): lut == nullptr disables it

@@ -84,6 +84,7 @@ struct Flat {
 	// structure with the same F; the generic term lists above stay valid either way.
 	int32_t tensor_F = 0;
 	int32_t tensor_K = 0;                 // F^N
+	bool tensor_uniform = false;          // cubic: in every leaf and dimension the 4 centres are spaced by exactly support/2 (one uniform knot vector)
 	std::vector<double> tl_center;        // [L * N * F] ascending per dimension
 	std::vector<double> tl_rcp;           // [L * N]     support (or 1/support when exact_rcp)
 	std::vector<int32_t> tl_slot;         // [L * F^N]   slot in the leaf's sorted support list, tensor order (dimension 0 fastest)

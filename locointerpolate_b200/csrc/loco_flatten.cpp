@@ -331,7 +331,18 @@ Status flatten(const Graph &g, Flat *out)
 				f.tl_row.push_back(f.term_row[(size_t)(t0 + hit[(size_t)j])]);
 			}
 		}
-		if (all) { f.tensor_F = F; f.tensor_K = (int32_t)KT; }
+		if (all) {
+			f.tensor_F = F; f.tensor_K = (int32_t)KT;
+			// uniform knots: c[j+1] - c[j] == support / 2 exactly, in every leaf and dimension (cubic only)
+			bool uni = cubic;
+			for (int64_t l = 0; l < L && uni; l++)
+				for (int i = 0; i < N && uni; i++) {
+					const double *c = &f.tl_center[((size_t)l * N + i) * F];
+					const double r = f.tl_rcp[(size_t)l * N + i], sup = f.exact_rcp ? 1.0 / r : r;
+					for (int j = 0; j + 1 < F; j++) uni = uni && (c[j + 1] - c[j] == 0.5 * sup);
+				}
+			f.tensor_uniform = uni;
+		}
 		else { f.tl_center.clear(); f.tl_rcp.clear(); f.tl_slot.clear(); f.tl_row.clear(); }
 		// ---- fold digits whose exchange never changes the value row (see loco_flat.h)
 		if (all) {

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) mesh_tensor_tiles_kernel(Device
 			sQi[q] = qi;
 			const double *blk = m.tl_block + (int64_t)leaf * m.tl_stride;
 			double f[NT][F];
-			tensor_factors<NT, CUBIC, EXACT>(blk, x, f);
+			tensor_factors<NT, CUBIC, EXACT>(blk, x, f, m.tensor_uniform != 0);
 #pragma unroll
 			for (int d = 0; d < NT; d++)
 #pragma unroll

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 			if (q < ig.nq) qi = load_sorted_row<NT>(xs + (int64_t)(ig.qbeg + q) * RS, x, NT);
 			sQi[ib * MM_Q + q] = qi;
 			double f[NT][F];
-			tensor_factors<NT, CUBIC, EXACT>(blk, x, f);
+			tensor_factors<NT, CUBIC, EXACT>(blk, x, f, m.tensor_uniform != 0);
 			// ---- folded factors g[d][c] = sum of the factors of the digits in class c (DeviceModel::fold_map), kept in shared
 			//      memory (column q is private to this lane) so that they can be indexed by a runtime class index
 			const uint8_t *fmap = m.fold_map + (int64_t)ig.leaf * NT * F;

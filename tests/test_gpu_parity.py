@@ -285,3 +285,23 @@ def test_mesh_valued_proto_file(golden, tmp_path):
     assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status)
     ok = status == 0
     assert_values_close(out[ok], o_out[ok], scale[ok])
+
+
+@pytest.mark.parametrize("name", ["cub3d_boot2", "cub2d_boot2", "cub3d_boot1_nocorner"])
+def test_uniform_knot_factors_equal_piecewise(golden, name):
+    """The four cubic factors of a dimension formed together from one spline parameter (uniform knots) against four
+    separate evaluations of the reference's piecewise form: rounding-level agreement, incl. the +-1e-6 acceptance band."""
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    o_out, _, o_status, scale = orc.eval(z["q"])
+    ok = o_status == 0
+    for path in (1, 4):
+        m.set_option("path", path)
+        m.set_option("uniform", 0)
+        a, _, _ = m.eval(z["q"])
+        m.set_option("uniform", 1)
+        b, _, _ = m.eval(z["q"])
+        assert_values_close(a[ok], o_out[ok], scale[ok])
+        assert_values_close(b[ok], o_out[ok], scale[ok])
+        assert np.abs(a[ok] - b[ok]).max() <= 1e-14 * max(1.0, np.abs(o_out[ok]).max())
