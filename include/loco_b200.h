@@ -217,6 +217,8 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
  *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
  *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto);
  *          "overlap" 1..4 (default 2): internal streams the chunks of path 4 are dealt over (forked from / joined to the caller's);
+ *          "fp32" 1: optional fp32 mode of the throughput path for scalar functions on tensor-product leaves (path 0/4): point
+ *                 location stays fp64 and bit-exact, basis polynomials and the weighted sum run in fp32 (1e-5 relative);
  *          "uniform" 1 (default): cubic tensor leaves with equally spaced centres form their four factors per dimension from one parameter;
  *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0) */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);

@@ -167,10 +167,10 @@ __device__ __forceinline__ void tensor_factors(const double *blk, const Coord<NT
 
 // sum over the F^(LEVEL+1) leading entries of v (dimension 0 fastest) of prod_{d<=LEVEL} f[d][j_d] * v[...]
 // -- LCFunctionValue::newFromWeightedSum with w_k = prod_d f[d][j_d], evaluated by sum factorisation.
-template <int F>
-__device__ __forceinline__ double pick_factor(const double (&row)[F], int j)
+template <int F, typename T = double>
+__device__ __forceinline__ T pick_factor(const T (&row)[F], int j)
 {
-	double r = row[0];
+	T r = row[0];
 #pragma unroll
 	for (int i = 1; i < F; i++) r = (i == j) ? row[i] : r;
 	return r;
@@ -344,5 +344,68 @@ __device__ __forceinline__ double term_value_smem(const double *cs, double wv, c
 	}
 	return value * wv;
 }
+
+// ---- optional fp32 mode (north star: 1e-5 relative) ---------------------------------------------------------------------
+// Point location stays in fp64 (leaf indices must be bit-exact) and so does the normalised distance u = (x-c)/s; the
+// basis polynomials, the products and the weighted sum run in fp32 on an fp32 copy of the leaf's sample values.
+__device__ __forceinline__ float linear_1d_f32(float u) { const float d = fabsf(u); return d <= 1.0f ? 1.0f - d : 0.0f; }
+__device__ __forceinline__ float cubic_1d_f32(float u)
+{
+	const float v = 2.0f * fabsf(u);
+	const float inner = fmaf(v * v, fmaf(3.0f, v, -6.0f), 4.0f);
+	const float w = 2.0f - v;
+	const float r = v < 1.0f ? inner : (v <= 2.0f ? w * w * w : 0.0f);
+	return r * (1.0f / 6.0f);
+}
+template <int NT, int F, int LEVEL>
+struct TensorContractF32 {
+	static __device__ __forceinline__ float run(const float *v, const float (&f)[NT][F], int stride)
+	{
+		float s = 0.0f;
+		if (ipow_c(F, LEVEL + 1) > 64) {
+			// outer levels of big tensors stay rolled (code size), as in TensorContract
+#pragma unroll 1
+			for (int j = 0; j < F; j++) s += pick_factor<F, float>(f[LEVEL], j) * TensorContractF32<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, f, stride / F);
+		} else {
+#pragma unroll
+			for (int j = 0; j < F; j++) s += f[LEVEL][j] * TensorContractF32<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, f, stride / F);
+		}
+		return s;
+	}
+};
+template <int NT, int F>
+struct TensorContractF32<NT, F, 0> {
+	static __device__ __forceinline__ float run(const float *v, const float (&f)[NT][F], int)
+	{
+		float s = 0.0f;
+		if (F == 4) {
+			const float4 p = *reinterpret_cast<const float4 *>(v);
+			s = f[0][0] * p.x + f[0][1] * p.y + f[0][2 % F] * p.z + f[0][3 % F] * p.w;
+		} else {
+			const float2 p = *reinterpret_cast<const float2 *>(v);
+			s = f[0][0] * p.x + f[0][1] * p.y;
+		}
+		return s;
+	}
+};
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double tensor_eval_scalar_f32(const DeviceModel &m, const double *blk, const float *vals, const Coord<NT> &x)
+{
+	constexpr int F = CUBIC ? 4 : 2;
+	float f[NT][F];
+#pragma unroll
+	for (int d = 0; d < NT; d++) {
+		const double r = blk[NT * F + d];
+		const double xv = x.get(d);
+#pragma unroll
+		for (int j = 0; j < F; j++) {
+			const double diff = xv - blk[d * F + j];
+			const float u = (float)(EXACT ? diff * r : diff / r);
+			f[d][j] = CUBIC ? cubic_1d_f32(u) : linear_1d_f32(u);
+		}
+	}
+	return (double)TensorContractF32<NT, F, NT - 1>::run(vals, f, m.tensor_K / F);
+}
+
 
 } // namespace loco

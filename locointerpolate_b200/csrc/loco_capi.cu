@@ -62,6 +62,7 @@ struct loco_model {
 	double *d_values = nullptr;
 	double *d_term_wv = nullptr;
 	double *d_tl_block = nullptr;
+	float *d_tl_vals_f32 = nullptr;
 	int64_t n_terms = 0;
 	int sm_count = 148;
 	int64_t device_bytes = 0;
@@ -133,7 +134,7 @@ int refresh_term_wv(loco_model *m)
 {
 	if (m->dm.D == 1) {
 		m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
-		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, nullptr);
+		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, m->d_tl_vals_f32, nullptr);
 	}
 	CUDA_OK(m, cudaGetLastError());
 	CUDA_OK(m, cudaDeviceSynchronize());
@@ -220,6 +221,14 @@ int build_device_model(loco_model *m)
 		m->d_tl_block = const_cast<double *>(dblk);
 		dm.tl_block = dblk;
 		if ((rc = upload(m, f.tl_row, &dm.tl_row))) return rc;
+		dm.tl_vals_f32 = nullptr;
+		if (f.D == 1) {  // fp32 copy of the leaf values for the optional fp32 mode
+			std::vector<float> zeros((size_t)f.L * K, 0.0f);
+			const float *dv = nullptr;
+			if ((rc = upload(m, zeros, &dv))) return rc;
+			m->d_tl_vals_f32 = const_cast<float *>(dv);
+			dm.tl_vals_f32 = dv;
+		}
 		std::vector<int32_t> fold_off = narrow(m, f.fold_off, &ok);
 		if ((rc = upload(m, fold_off, &dm.fold_off))) return rc;
 		if ((rc = upload(m, f.fold_row, &dm.fold_row))) return rc;
@@ -324,7 +333,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 			int k = 0;
 			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
 				const int64_t n = std::min(chunk, Q - o);
-				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw[k], m->sm_count, run_on[k]);
+				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw[k], m->sm_count, m->opt_fp32 != 0, run_on[k]);
 			}
 			if (ns > 1) {
 				// join: the caller's stream continues when all of them are done

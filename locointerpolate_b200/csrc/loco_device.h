@@ -41,6 +41,7 @@ struct DeviceModel {
 	//   [N*F centres | N supports-or-reciprocals | pad to even | F^N sample values in tensor order (D == 1 only)]
 	int32_t tensor_F, tensor_K, tl_stride, tl_voff, tensor_uniform;
 	const double *tl_block;           // [L * tl_stride]
+	const float *tl_vals_f32;         // [L * F^N] fp32 copy of the leaf values in tensor order (optional fp32 mode, D == 1)
 	const int32_t *tl_row;            // [L * F^N] value rows in tensor order
 	// locate grid (Flat::lut): lut == nullptr disables it
 	const uint32_t *lut;
@@ -131,7 +132,7 @@ struct SortWork {
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
-int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, cudaStream_t st);
+int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);
 int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, int tile_q,
@@ -162,6 +163,6 @@ size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk);
 SortedWork carve_sorted_work(const DeviceModel &m, void *base);
 int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t st);
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
-                                    int sm_count, cudaStream_t st);
+                                    int sm_count, bool fp32, cudaStream_t st);
 
 } // namespace loco

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) sorted_scatter_kernel(DeviceModel m, cons
 // Persistent threads: thread t evaluates records t, t+T, t+2T, ...  While record i is being evaluated, record i+T is
 // already in registers with the lines of ITS leaf block on their way into L1, and the load of record i+2T is in flight:
 // the two dependent memory round trips of a query (record -> leaf block) overlap the arithmetic of its predecessors.
-template <int NT, bool CUBIC, bool EXACT, bool TENSOR>
+template <int NT, bool CUBIC, bool EXACT, bool TENSOR, bool FP32>
 __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_kernel(DeviceModel m, const double *__restrict__ xs, const int32_t *__restrict__ cursor,
                                                            double *__restrict__ out)
 {
@@ -216,6 +216,12 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 				// pull the lines of the NEXT record's leaf block into L1 before starting on this record's arithmetic
 				const int32_t nleaf = (int32_t)(__double_as_longlong(b[RSmax - 1]) >> 32);
 				const char *blk_bytes = reinterpret_cast<const char *>(m.tl_block + (int64_t)nleaf * m.tl_stride);
+				if constexpr (FP32) {
+					// centres / supports from the fp64 block, values from the fp32 copy
+					const char *val_bytes = reinterpret_cast<const char *>(m.tl_vals_f32 + (int64_t)nleaf * m.tensor_K);
+					for (int o = 0; o < m.tl_voff * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk_bytes + o));
+					for (int o = 0; o < m.tensor_K * 4; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(val_bytes + o));
+				} else
 				for (int o = 0; o < m.tl_stride * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk_bytes + o));
 			}
 #pragma unroll
@@ -224,7 +230,8 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 		}
 		double r = 0.0;
 		if constexpr (TENSOR) {
-			r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf * m.tl_stride, x);
+			if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf * m.tl_stride, m.tl_vals_f32 + (int64_t)leaf * m.tensor_K, x);
+			else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf * m.tl_stride, x);
 		} else {
 			// LCSample::getInterpolationWeight / newFromWeightedSum over the leaf's term list, as in eval_scalar_direct_kernel,
 			// with weight_ * val pre-multiplied per term (term_wv)
@@ -250,14 +257,15 @@ void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t
 	sorted_scatter_kernel<NT><<<(unsigned)((Q + 256 * kScatterItems - 1) / (256 * kScatterItems)), 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
 }
 template <int NT, bool CUBIC, bool EXACT>
-void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, cudaStream_t st)
+void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, bool fp32, cudaStream_t st)
 {
 	const unsigned g = (unsigned)std::min<int64_t>((Q + 255) / 256, (int64_t)sm_count * 8);
 	LOCO_KERNEL("sorted_eval", st);
 	if constexpr (NT > 0) {
-		if (m.tensor_F > 0) { sorted_eval_kernel<NT, CUBIC, EXACT, true><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
+		if (m.tensor_F > 0 && fp32 && m.tl_vals_f32) { sorted_eval_kernel<NT, CUBIC, EXACT, true, true><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
+		if (m.tensor_F > 0) { sorted_eval_kernel<NT, CUBIC, EXACT, true, false><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
 	}
-	sorted_eval_kernel<NT, CUBIC, EXACT, false><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out);
+	sorted_eval_kernel<NT, CUBIC, EXACT, false, false><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out);
 }
 
 } // namespace
@@ -288,7 +296,7 @@ int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t 
 }
 
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
-                                    int sm_count, cudaStream_t st)
+                                    int sm_count, bool fp32, cudaStream_t st)
 {
 	static const bool scan_smem_set = [] {
 		cudaFuncSetAttribute(sorted_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kScanSeg + kScanSeg / 32) * sizeof(int)));
@@ -301,8 +309,8 @@ int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64
 	case NT:                                                                                                 \
 		run_count<NT>(m, q, Q, leaf, status, out, w, st);                                                    \
 		run_scatter<NT>(m, q, Q, leaf, status, w, st);                                                       \
-		if (cubic) { if (exact) run_eval<NT, true, true>(m, Q, w, out, sm_count, st); else run_eval<NT, true, false>(m, Q, w, out, sm_count, st); } \
-		else { if (exact) run_eval<NT, false, true>(m, Q, w, out, sm_count, st); else run_eval<NT, false, false>(m, Q, w, out, sm_count, st); }     \
+		if (cubic) { if (exact) run_eval<NT, true, true>(m, Q, w, out, sm_count, fp32, st); else run_eval<NT, true, false>(m, Q, w, out, sm_count, fp32, st); } \
+		else { if (exact) run_eval<NT, false, true>(m, Q, w, out, sm_count, fp32, st); else run_eval<NT, false, false>(m, Q, w, out, sm_count, fp32, st); }     \
 		break;
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 		LOCO_SCASE(0) LOCO_SCASE(1) LOCO_SCASE(2) LOCO_SCASE(3) LOCO_SCASE(4) LOCO_SCASE(5) LOCO_SCASE(6) LOCO_SCASE(7) LOCO_SCASE(8)

@@ -37,19 +37,21 @@ __global__ void __launch_bounds__(256) eval_tensor_direct_kernel(DeviceModel m, 
 }
 
 // tl_block[leaf][voff + j] = values[tl_row[leaf][j]]   (scalar functions; after every change of the value table)
-__global__ void tensor_vals_kernel(DeviceModel m, double *__restrict__ tl_block)
+__global__ void tensor_vals_kernel(DeviceModel m, double *__restrict__ tl_block, float *__restrict__ tl_vals_f32)
 {
 	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (e >= (int64_t)m.L * m.tensor_K) return;
 	const int64_t leaf = e / m.tensor_K, j = e - leaf * m.tensor_K;
-	tl_block[leaf * m.tl_stride + m.tl_voff + j] = m.values[(int64_t)m.tl_row[e] * m.value_stride];
+	const double v = m.values[(int64_t)m.tl_row[e] * m.value_stride];
+	tl_block[leaf * m.tl_stride + m.tl_voff + j] = v;
+	if (tl_vals_f32) tl_vals_f32[e] = (float)v;
 }
 
-int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, cudaStream_t st)
+int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st)
 {
 	if (m.tensor_F <= 0 || m.D != 1) return 0;
 	const int64_t n = (int64_t)m.L * m.tensor_K;
-	tensor_vals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, tl_block);
+	tensor_vals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, tl_block, tl_vals_f32);
 	return 1;
 }
 

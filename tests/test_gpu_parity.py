@@ -305,3 +305,30 @@ def test_uniform_knot_factors_equal_piecewise(golden, name):
         assert_values_close(a[ok], o_out[ok], scale[ok])
         assert_values_close(b[ok], o_out[ok], scale[ok])
         assert np.abs(a[ok] - b[ok]).max() <= 1e-14 * max(1.0, np.abs(o_out[ok]).max())
+
+
+@pytest.mark.parametrize("N,basis,level", [(3, capi.CUBIC, 4), (2, capi.CUBIC, 5), (4, capi.LINEAR, 3)])
+def test_optional_fp32_mode(N, basis, level):
+    """north star: interpolated values within 1e-5 relative in the optional fp32 mode; leaf indices stay bit-exact."""
+    torch = _torch()
+
+    def f(p):
+        return 1 + np.sin(3 * p + np.arange(len(p))).sum()
+    m = capi.Model.bootstrap(N, basis, level, 1, True, fn=f, device=0)
+    Q = 400_000
+    tq = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for fp32 in (0, 1):
+        m.set_option("path", 4)
+        m.set_option("fp32", fp32)
+        out = torch.empty(Q, dtype=torch.float64, device="cuda")
+        leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+        status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+        m.eval_device(tq.data_ptr(), Q, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+        torch.cuda.synchronize()
+        res[fp32] = (out.cpu().numpy(), leaf.cpu().numpy(), status.cpu().numpy())
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    diff = np.abs(res[0][0] - res[1][0])
+    assert diff.max() > 0, "the fp32 mode did not run"
+    assert (diff <= 1e-5 * np.maximum(np.abs(res[0][0]), 1.0)).all(), diff.max()
