@@ -61,6 +61,7 @@ struct loco_model {
 	std::vector<void *> allocs;
 	double *d_values = nullptr;
 	double *d_term_wv = nullptr;
+	double *d_mterm_wv = nullptr;
 	double *d_tl_block = nullptr;
 	float *d_tl_vals_f32 = nullptr;
 	int64_t n_terms = 0;
@@ -134,6 +135,7 @@ int refresh_term_wv(loco_model *m)
 {
 	if (m->dm.D == 1) {
 		m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
+		m->launches += launch_update_mterm_wv(m->dm, m->d_mterm_wv, nullptr);
 		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, m->d_tl_vals_f32, nullptr);
 	}
 	CUDA_OK(m, cudaGetLastError());
@@ -182,6 +184,23 @@ int build_device_model(loco_model *m)
 	if ((rc = upload(m, f.term_w, &dm.term_w))) return rc;
 	if ((rc = upload(m, f.term_slot, &dm.term_slot))) return rc;
 	if ((rc = upload(m, f.term_row, &dm.term_row))) return rc;
+	dm.mterm_off = nullptr; dm.n_mterms = 0;
+	if (!f.mterm_off.empty()) {
+		std::vector<int32_t> moff = narrow(m, f.mterm_off, &ok), roff = narrow(m, f.mrun_off, &ok);
+		if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
+		dm.n_mterms = f.mterm_off.back();
+		if ((rc = upload(m, moff, &dm.mterm_off))) return rc;
+		if ((rc = upload(m, f.mterm_cs, &dm.mterm_cs, 2))) return rc;
+		if ((rc = upload(m, roff, &dm.mrun_off))) return rc;
+		if ((rc = upload(m, f.mrun_term, &dm.mrun_term))) return rc;
+		std::vector<double> zeros((size_t)dm.n_mterms + 2, 0.0);
+		const double *dwv = nullptr;
+		if ((rc = upload(m, zeros, &dwv))) return rc;
+		m->d_mterm_wv = const_cast<double *>(dwv);
+		dm.mterm_wv = dwv;
+		std::vector<double>().swap(f.mterm_cs);
+		std::vector<int32_t>().swap(f.mrun_term);
+	}
 	std::vector<int32_t> dterm_off = narrow(m, f.dterm_off, &ok);
 	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
 	if ((rc = upload(m, dterm_off, &dm.dterm_off))) return rc;

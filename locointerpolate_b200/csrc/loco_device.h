@@ -33,6 +33,11 @@ struct DeviceModel {
 	const int32_t *term_row;          // [sum T]
 	const double *term_wv;            // [sum T + 2] weight * value of the owning sample (scalar functions only)
 	const double *values;             // [R * value_stride]
+	// merged terms (Flat::mterm_*; mterm_off == nullptr: not built).  mterm_wv[t] = sum over the run of weight * value.
+	const int32_t *mterm_off;
+	const double *mterm_cs, *mterm_wv;
+	const int32_t *mrun_off, *mrun_term;
+	int64_t n_mterms;
 	// derivative-only extra terms of the linear basis (CSR by leaf; see Flat::dterm_*)
 	const int32_t *dterm_off;
 	const double *dterm_cs, *dterm_w;
@@ -132,6 +137,7 @@ struct SortWork {
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
+int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t st);
 int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);

@@ -66,6 +66,14 @@ struct Flat {
 	std::vector<int32_t> term_slot;    // [sum T] position of the owning sample in the leaf's support list (ascending)
 	std::vector<int32_t> term_row;     // [sum T] = sup_row[sup_off[leaf] + slot]
 
+	// merged terms (scalar functions): within a leaf, basis functions with bit-identical (centre, support) owned by different
+	// samples are one term  (sum_e weight_e * val_e) * B(x)  -- refineCell re-attaches equal functions to several samples
+	// (LCAdaptiveGrid.cpp:825-862), so adaptive trees carry each function ~3 times.  Built only when it saves >= 25 %.
+	std::vector<int64_t> mterm_off;    // [L+1] CSR by leaf into the merged terms
+	std::vector<double> mterm_cs;      // [M * 2N]
+	std::vector<int64_t> mrun_off;     // [M+1] CSR: the original terms merged into each
+	std::vector<int32_t> mrun_term;    // [sum T] indices into the term arrays above
+
 	// derivative-only extra terms (linear basis; see loco_flatten.cpp): hats outside the leaf that the reference's
 	// LCLinearBSpline::evalDeriv still counts because it compares the SIGNED distance with 1
 	std::vector<int64_t> dterm_off;    // [L+1]

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <numeric>
 
 namespace loco {
@@ -277,6 +278,37 @@ Status flatten(const Graph &g, Flat *out)
 		f.term_off.push_back((int64_t)f.term_w.size());
 		f.dterm_off.push_back((int64_t)f.dterm_w.size());
 		f.max_terms = std::max<int32_t>(f.max_terms, (int32_t)(f.term_off[(size_t)l + 1] - f.term_off[(size_t)l]));
+	}
+
+	// ---- merged terms for scalar functions (see loco_flat.h) ---------------------------------------------------------
+	if (g.D == 1) {
+		std::vector<int64_t> order;
+		const size_t row_bytes = sizeof(double) * 2 * (size_t)N;
+		f.mterm_off.assign(1, 0);
+		f.mrun_off.assign(1, 0);
+		for (int64_t l = 0; l < L; l++) {
+			const int64_t t0 = f.term_off[(size_t)l], t1 = f.term_off[(size_t)l + 1];
+			order.resize((size_t)(t1 - t0));
+			std::iota(order.begin(), order.end(), t0);
+			std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+				const int c = memcmp(&f.term_cs[(size_t)a * 2 * N], &f.term_cs[(size_t)b * 2 * N], row_bytes);
+				return c < 0 || (c == 0 && a < b);
+			});
+			for (size_t i = 0; i < order.size(); i++) {
+				const bool same = i > 0 && memcmp(&f.term_cs[(size_t)order[i] * 2 * N], &f.term_cs[(size_t)order[i - 1] * 2 * N], row_bytes) == 0;
+				if (!same) {
+					if (i > 0) f.mrun_off.push_back((int64_t)f.mrun_term.size());
+					f.mterm_cs.insert(f.mterm_cs.end(), f.term_cs.begin() + order[i] * 2 * N, f.term_cs.begin() + (order[i] + 1) * 2 * N);
+				}
+				f.mrun_term.push_back((int32_t)order[i]);
+			}
+			if (!order.empty()) f.mrun_off.push_back((int64_t)f.mrun_term.size());
+			f.mterm_off.push_back((int64_t)f.mterm_cs.size() / (2 * N));
+		}
+		const int64_t M = f.mterm_off.back(), T = f.term_off.back();
+		if (T >= (int64_t)0x7fffffff || M * 4 > T * 3) {  // not worth a second copy of the term list
+			f.mterm_off.clear(); f.mterm_cs.clear(); f.mrun_off.clear(); f.mrun_term.clear();
+		}
 	}
 
 	// ---- tensor-product structure (see loco_flat.h) ---------------------------------------------------

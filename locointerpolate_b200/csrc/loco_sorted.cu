@@ -235,8 +235,13 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 		} else {
 			// LCSample::getInterpolationWeight / newFromWeightedSum over the leaf's term list, as in eval_scalar_direct_kernel,
 			// with weight_ * val pre-multiplied per term (term_wv)
-			for (int t = __ldg(m.term_off + leaf), t1 = __ldg(m.term_off + leaf + 1); t < t1; t++)
-				r += term_value<NT, CUBIC, EXACT>(m.term_cs + (int64_t)t * 2 * N, __ldg(m.term_wv + t), x, N);
+			if (m.mterm_off) {  // merged: one term per distinct basis function of the leaf
+				for (int t = __ldg(m.mterm_off + leaf), t1 = __ldg(m.mterm_off + leaf + 1); t < t1; t++)
+					r += term_value<NT, CUBIC, EXACT>(m.mterm_cs + (int64_t)t * 2 * N, __ldg(m.mterm_wv + t), x, N);
+			} else {
+				for (int t = __ldg(m.term_off + leaf), t1 = __ldg(m.term_off + leaf + 1); t < t1; t++)
+					r += term_value<NT, CUBIC, EXACT>(m.term_cs + (int64_t)t * 2 * N, __ldg(m.term_wv + t), x, N);
+			}
 		}
 		out[qi] = r;
 	}

@@ -350,6 +350,25 @@ SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base)
 	return w;
 }
 
+// mterm_wv[t] = sum over the merged run of term_w * value   (summed in run order: ascending original term index)
+__global__ void mterm_wv_kernel(DeviceModel m, double *__restrict__ mterm_wv)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m.n_mterms) return;
+	double s = 0.0;
+	for (int e = m.mrun_off[t], e1 = m.mrun_off[t + 1]; e < e1; e++) {
+		const int32_t o = m.mrun_term[e];
+		s += m.term_w[o] * m.values[(int64_t)m.term_row[o] * m.value_stride];
+	}
+	mterm_wv[t] = s;
+}
+int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t st)
+{
+	if (!m.mterm_off || m.n_mterms <= 0) return 0;
+	mterm_wv_kernel<<<(unsigned)((m.n_mterms + 255) / 256), 256, 0, st>>>(m, mterm_wv);
+	return 1;
+}
+
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st)
 {
 	if (T <= 0) return 0;
