@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--level", type=int, default=-1, help="override the workload's bootstrap level (experiments)")
     ap.add_argument("--queries", type=int, default=0, help="queries per step per GPU (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,6 +187,9 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.queries:
         w["Q"] = args.queries
+    if args.level >= 0:
+        w["level"] = args.level
+        w["desc"] += f" [bootstrap level overridden to {args.level}]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

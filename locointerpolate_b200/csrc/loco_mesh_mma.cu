@@ -66,8 +66,8 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, i
 	g.leaf = lo;
 	g.qbeg = __ldg(offset + lo) + (int32_t)(tile - __ldg(tile_off + lo)) * MM_Q;
 	g.nq = min(MM_Q, __ldg(offset + lo + 1) - g.qbeg);
-	g.dc0 = (int32_t)dgroup * dg;
-	g.n_dc = min(dg, n_dchunks - g.dc0);
+	g.dc0 = (int32_t)dgroup * (dg & 0xfff);
+	g.n_dc = min(dg & 0xfff, n_dchunks - g.dc0);
 	g.row0 = __ldg(fold_off + lo);
 	g.K = __ldg(fold_off + lo + 1) - g.row0;
 	return g;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	double *sL = sF + NT * F * MM_Q;                               // [LOWK][MM_Q]   producer only
 	int32_t *sQi = reinterpret_cast<int32_t *>(sL + LOWK * MM_Q);  // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
 	__shared__ __align__(8) uint64_t full_bar[MM_NS], empty_bar[MM_NS], item_bar[2];
+	__shared__ ItemGeom s_item[2];  // the producers locate the item's leaf (a binary search over tile offsets); the consumers read it here
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < MM_NS; i++) { mbar_init(&full_bar[i], MM_PRODUCERS); mbar_init(&empty_bar[i], MM_CONSUMERS); }
 		mbar_init(&item_bar[0], MM_CONSUMERS); mbar_init(&item_bar[1], MM_CONSUMERS);
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	// `out` (a ring the caller consumes in leaf order) instead of row (query index)
 	const int32_t L = m.L;
 	const int64_t n_tiles = n_tiles_arg >= 0 ? n_tiles_arg : (int64_t)tile_off[L];
-	const int32_t n_dgroups = (n_dchunks + dg - 1) / dg;
+	const int32_t n_dgroups = (n_dchunks + (dg & 0xfff) - 1) / (dg & 0xfff);
 	const int64_t total = n_tiles * n_dgroups;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 			int32_t qi = -1;
 			if (q < ig.nq) qi = load_sorted_row<NT>(xs + (int64_t)(ig.qbeg + q) * RS, x, NT);
 			sQi[ib * MM_Q + q] = qi;
+			if (pw == 0 && lane == 0) s_item[ib] = ig;  // published by the arrival on the item's first stage barrier
 			double f[NT][F];
 			tensor_factors<NT, CUBIC, EXACT>(blk, x, f, m.tensor_uniform != 0);
 			// ---- folded factors g[d][c] = sum of the factors of the digits in class c (DeviceModel::fold_map), kept in shared
@@ -259,11 +261,14 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	const int wq = warp >> 2, wd = warp & 3;   // 2 x 4 warps: warp tile = 32 queries x 32 components = 4 x 4 MMA tiles
 	const int fr = lane >> 2, fc = lane & 3;   // fragment coordinates: A[fr][fc], B[fc][fr], C[fr][2*fc .. 2*fc+1]
 	const bool vec_out = ((out_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+	const bool wide_out = ((out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);  // rows 32-byte aligned
 	uint32_t g = 0, it = 0;
 	double acc[4][4][2];  // [query block mi][component block ni][2]
 	for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-		const ItemGeom ig = item_geometry(item, tile0, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
 		const int ib = it & 1;
+		// the first stage of the item being full means its geometry (and query indices, weights) are in shared memory
+		mbar_wait(&full_bar[g % MM_NS], (g / MM_NS) & 1u);
+		const ItemGeom ig = s_item[ib];
 		const int32_t K = ig.K;
 		const int n_stages = (K + MM_K - 1) / MM_K;
 		const int n_steps = ig.n_dc * n_stages;
@@ -303,10 +308,30 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				// ---- epilogue of a chunk: each output element is written exactly once; a fragment row is 2 consecutive doubles
 				const int32_t d0 = (ig.dc0 + dc) * MM_D;
 				const int32_t nd = min(MM_D, m.D - d0);
+				if (wide_out && nd == MM_D) {
+					// 256-bit stores of FULL 128-byte lines: a lane pair (fc, fc^1) swaps one 8x8 fragment row half so that each
+					// lane owns 4 consecutive components of one row; the 4 lanes of a row then cover 16 consecutive doubles
+					const bool odd = fc & 1;
+#pragma unroll
+					for (int mi = 0; mi < 4; mi++) {
+						const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
+						const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
+						double *o = out + orow * out_stride + d0 + wd * 32;
+#pragma unroll
+						for (int p = 0; p < 2; p++) {
+							const int n0 = 2 * p, n1 = 2 * p + 1;
+							const double s0 = odd ? acc[mi][n0][0] : acc[mi][n1][0], s1 = odd ? acc[mi][n0][1] : acc[mi][n1][1];
+							const double r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+							if (qi < 0 || (dg & 0x1000)) continue;
+							if (odd) st_stream_f64x4(o + n1 * 8 + 2 * (fc - 1), r0, r1, acc[mi][n1][0], acc[mi][n1][1]);
+							else st_stream_f64x4(o + n0 * 8 + 2 * fc, acc[mi][n0][0], acc[mi][n0][1], r0, r1);
+						}
+					}
+				} else {
 #pragma unroll
 				for (int mi = 0; mi < 4; mi++) {
 					const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
-					if (qi < 0) continue;
+					if (qi < 0 || (dg & 0x1000)) continue;  // EXPERIMENT: bit 12 of dg disables the result stores
 					const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
 					double *o = out + orow * out_stride + d0;
 #pragma unroll
@@ -319,6 +344,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 							if (col + 1 < nd) o[col + 1] = acc[mi][ni][1];
 						}
 					}
+				}
 				}
 			}
 		}
@@ -374,6 +400,7 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	const int64_t slice_cap = ((int64_t)28 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
 	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
 	if (const char *e = getenv("LOCO_MESH_DG")) dg = std::max(1, std::min(atoi(e), n_dchunks));  // tuning experiments
+	if (getenv("LOCO_MESH_NOSTORE")) dg |= 0x1000;
 	const int grid = sm_count * 2;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \

@@ -58,6 +58,11 @@ __device__ __forceinline__ void st_stream_f64x2(double *p, double a, double b, u
 {
 	asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(policy) : "memory");
 }
+// 256-bit streaming store (sm_100: st.global.v4.f64), 32-byte aligned
+__device__ __forceinline__ void st_stream_f64x4(double *p, double a, double b, double c, double d)
+{
+	asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
