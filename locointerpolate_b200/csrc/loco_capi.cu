@@ -46,7 +46,9 @@ const int kSlots = 3;  // pipeline depth of the host-buffer path
 struct Workspace {
 	cudaStream_t stream = nullptr;
 	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr, *sorted = nullptr;
-	void *sortedx[3] = {nullptr, nullptr, nullptr};  // workspaces of the additional streams of the sorted path
+	void *sortedx[3] = {nullptr, nullptr, nullptr};
+	void *woff = nullptr;  // weight-block offsets of the generic mesh path
+	size_t woff_b = 0;  // workspaces of the additional streams of the sorted path
 	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0, sorted_b = 0, sortedx_b[3] = {0, 0, 0};
 };
 
@@ -390,6 +392,22 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		CUDA_OK(m, cudaGetLastError());
 		return LOCO_OK;
 	}
+	// mesh-valued on generic leaves (adaptive trees): sort by leaf, weights into a leaf-major matrix, fp64 MMA tiles (loco_mesh_gen.cu)
+	if (!in_cube && m->opt_path != 1 && m->opt_path != 3 && !m->opt_mesh_simt && dm.max_support > 0 &&
+	    mesh_generic_weight_doubles(dm, Q) * sizeof(double) <= ((size_t)24 << 30)) {
+		int rc;
+		if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+		if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+		if ((rc = grow(m, &w.misc, &w.misc_b, sort_work_bytes(dm, Q)))) return rc;
+		if ((rc = grow(m, &w.W, &w.W_b, mesh_generic_weight_doubles(dm, Q) * sizeof(double)))) return rc;
+		if ((rc = grow(m, &w.woff, &w.woff_b, ((size_t)dm.L + 1) * sizeof(int64_t)))) return rc;
+		const SortWork sw = carve_sort_work(dm, Q, w.misc);
+		m->launches += launch_sort_by_leaf(dm, q, Q, leaf, status, sw, mesh_generic_tile_queries(), nullptr, st);
+		m->launches += launch_mesh_generic_mma(dm, sw, leaf, Q, (int64_t *)w.woff, (double *)w.W, out, out_stride, m->sm_count, 0, -1, -1, false, st);
+		m->launches += launch_mesh_nan_rows(dm, status, Q, out, out_stride, st);
+		CUDA_OK(m, cudaGetLastError());
+		return LOCO_OK;
+	}
 	// generic mesh-valued path: weights, then the weighted gather-sum, in chunks that bound the weight scratch
 	const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(Q, ((int64_t)256 << 20) / ((int64_t)dm.max_support * 8)));
 	int rc;
@@ -530,7 +548,7 @@ void loco_free(loco_model_t *m)
 	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
 	for (int s = 0; s < kSlots; s++) {
 		Workspace &w = m->ws[s];
-		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted, w.sortedx[0], w.sortedx[1], w.sortedx[2]}) if (p) cudaFree(p);
+		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted, w.sortedx[0], w.sortedx[1], w.sortedx[2], w.woff}) if (p) cudaFree(p);
 		if (w.stream) cudaStreamDestroy(w.stream);
 	}
 	delete m;

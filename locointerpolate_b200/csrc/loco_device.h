@@ -155,6 +155,12 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 // checksum[query index of sorted position p] = sum_j ring[p - p0][j] * (1 + j % 7) for p in [p0, p0 + n); queries with an error status get NaN
 int launch_checksum_sorted(const DeviceModel &m, const double *ring, int64_t ring_stride, const SortWork &w, int64_t p0, int64_t n, double *checksum, cudaStream_t st);
 int launch_checksum_bad(const uint8_t *status, int64_t Q, double *checksum, cudaStream_t st);
+// fp64 MMA tiles for mesh-valued functions on GENERIC leaves (loco_mesh_gen.cu): weights from the term lists into global memory,
+// then the same TMA / DMMA tile pipeline; same sorted input, tiles of mesh_generic_tile_queries()
+int mesh_generic_tile_queries();
+size_t mesh_generic_weight_doubles(const DeviceModel &m, int64_t Q);
+int launch_mesh_generic_mma(const DeviceModel &m, const SortWork &w, const int32_t *leaf_of, int64_t Q, int64_t *woff, double *W, double *out,
+                            int64_t out_stride, int sm_count, int64_t tile0, int64_t n_tiles, int64_t ring_base, bool weights_ready, cudaStream_t st);
 int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortWork &w,
                              int sm_count, cudaStream_t st);
 
