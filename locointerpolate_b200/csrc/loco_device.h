@@ -132,6 +132,7 @@ struct SortWork {
 	int32_t *tile_off;  // [L+1] tile offsets
 	int32_t *rank;      // [Q] arrival rank of each query inside its leaf bucket
 	int32_t *idx;       // unused (kept for layout compatibility)
+	int32_t *tile_leaf; // [Q / 32 + L + 1] leaf of every tile (so that a tile's leaf is one load, not a binary search over tile_off)
 	double *xs;         // [Q * row] sorted query records: N cube coordinates + original index, 32-byte sectors
 };
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q);

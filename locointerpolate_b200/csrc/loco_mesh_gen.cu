@@ -96,15 +96,12 @@ __global__ void __launch_bounds__(256) weights_sorted_kernel(DeviceModel m, cons
 }
 
 __device__ __forceinline__ GenGeom gen_geometry(const DeviceModel &m, int64_t item, int64_t tile0, int64_t n_tiles, int32_t n_dchunks, int dg,
-                                                const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off, const int64_t *__restrict__ woff)
+                                                const int32_t *__restrict__ offset, const int32_t *__restrict__ tile_off, const int64_t *__restrict__ woff,
+                                                const int32_t *__restrict__ tile_leaf)
 {
 	GenGeom g;
 	const int64_t dgroup = item / n_tiles, tile = tile0 + (item - dgroup * n_tiles);
-	int32_t lo = 0, hi = m.L;  // last leaf whose first tile is <= tile
-	while (lo < hi) {
-		const int32_t mid = (lo + hi) >> 1;
-		if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
-	}
+	const int32_t lo = __ldg(tile_leaf + tile);  // leaf of the tile (SortWork::tile_leaf)
 	g.leaf = lo;
 	const int32_t lofs = __ldg(offset + lo), n = __ldg(offset + lo + 1) - lofs;
 	g.qoff = (int32_t)(tile - __ldg(tile_off + lo)) * MG_Q;
@@ -121,7 +118,8 @@ __device__ __forceinline__ GenGeom gen_geometry(const DeviceModel &m, int64_t it
 } // namespace
 
 __global__ void __launch_bounds__(MG_THREADS, 2) mesh_generic_mma_kernel(DeviceModel m, const double *__restrict__ xs, int32_t rs, const int32_t *__restrict__ offset,
-                                                                          const int32_t *__restrict__ tile_off, const int64_t *__restrict__ woff,
+                                                                          const int32_t *__restrict__ tile_off, const int32_t *__restrict__ tile_leaf,
+                                                                          const int64_t *__restrict__ woff,
                                                                           const double *__restrict__ W, double *__restrict__ out, int64_t out_stride,
                                                                           int32_t n_dchunks, int32_t dg, int64_t tile0, int64_t n_tiles_arg, int64_t ring_base)
 {
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(MG_THREADS, 2) mesh_generic_mma_kernel(DeviceM
 		const uint64_t keep = l2_policy_evict_last();
 		uint32_t g = 0, it = 0;
 		for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-			const GenGeom ig = gen_geometry(m, item, tile0, n_tiles, n_dchunks, dg, offset, tile_off, woff);
+			const GenGeom ig = gen_geometry(m, item, tile0, n_tiles, n_dchunks, dg, offset, tile_off, woff, tile_leaf);
 			const int ib = it & 1;
 			mbar_wait(&item_bar[ib], ((it >> 1) & 1u) ^ 1u);  // the consumers are done with this item buffer (two items ago)
 #pragma unroll
@@ -300,7 +298,7 @@ int launch_mesh_generic_mma(const DeviceModel &m, const SortWork &w, const int32
 	(void)attr_set;
 	if (n_tiles < 0) tile0 = 0;
 	LOCO_KERNEL("mesh_generic_mma", st);
-	mesh_generic_mma_kernel<<<sm_count * 2, MG_THREADS, smem, st>>>(m, w.xs, sorted_row_doubles(m.N), w.offset, w.tile_off, woff, W, out, out_stride, n_dchunks, dg,
+	mesh_generic_mma_kernel<<<sm_count * 2, MG_THREADS, smem, st>>>(m, w.xs, sorted_row_doubles(m.N), w.offset, w.tile_off, w.tile_leaf, woff, W, out, out_stride, n_dchunks, dg,
 	                                                                tile0, n_tiles, ring_base);
 	return launched + 1;
 }

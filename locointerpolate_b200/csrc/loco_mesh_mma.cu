@@ -40,6 +40,8 @@ constexpr int MM_D = 128;     // value components per chunk
 constexpr int MM_K = 16;      // value rows per stage
 constexpr int MM_NS_MULTI = 3; // stages in flight when a chunk needs several stages (2 CTAs of ~98 KB per SM)
 constexpr int MM_NS_ONE = 4;   // ... when all K <= 16 rows fit one stage: the weights are per item, a stage is value rows only
+constexpr bool MM_TMA_STORE = false;  // results through shared memory + TMA bulk stores (measured: no gain over direct 256-bit stores, costs a stage)
+constexpr int MM_STG_LD = 40;  // row stride (doubles) of a warp's 8 x 32 result staging block: conflict-free 128-bit stores, 16-byte aligned rows
 constexpr int MM_CONSUMERS = 8;
 constexpr int MM_PRODUCERS = MM_Q / 32;  // one producer lane per query of the tile
 constexpr int MM_THREADS = (MM_CONSUMERS + MM_PRODUCERS) * 32;
@@ -54,15 +56,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc, row0, K; };  // row0, K: the leaf's folded row list in DeviceModel::fold_row
 // item -> (chunk group, tile) -> leaf and query range; identical arithmetic in the producer and in every consumer warp
 __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, int64_t n_tiles, int32_t L, int32_t n_dchunks, int dg, const int32_t *__restrict__ offset,
-                                                  const int32_t *__restrict__ tile_off, const int32_t *__restrict__ fold_off)
+                                                  const int32_t *__restrict__ tile_off, const int32_t *__restrict__ fold_off, const int32_t *__restrict__ tile_leaf)
 {
 	ItemGeom g;
 	const int64_t dgroup = item / n_tiles, tile = tile0 + (item - dgroup * n_tiles);
-	int32_t lo = 0, hi = L;  // last leaf whose first tile is <= tile
-	while (lo < hi) {
-		const int32_t mid = (lo + hi) >> 1;
-		if (__ldg(tile_off + mid + 1) <= tile) lo = mid + 1; else hi = mid;
-	}
+	const int32_t lo = __ldg(tile_leaf + tile);  // leaf of the tile (SortWork::tile_leaf)
 	g.leaf = lo;
 	g.qbeg = __ldg(offset + lo) + (int32_t)(tile - __ldg(tile_off + lo)) * MM_Q;
 	g.nq = min(MM_Q, __ldg(offset + lo + 1) - g.qbeg);
@@ -76,7 +74,8 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, i
 
 template <int NT, bool CUBIC, bool EXACT, bool ONE>
 __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceModel m, const double *__restrict__ xs, const int32_t *__restrict__ offset,
-                                                                         const int32_t *__restrict__ tile_off, double *__restrict__ out,
+                                                                         const int32_t *__restrict__ tile_off, const int32_t *__restrict__ tile_leaf,
+                                                                         double *__restrict__ out,
                                                                          int64_t out_stride, int32_t n_dchunks, int32_t dg, int64_t tile0, int64_t n_tiles_arg,
                                                                          int64_t ring_base)
 {
@@ -95,6 +94,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	double *sF = sW + MM_NW * MM_K * MM_LDW;                       // [NT*F][MM_Q]   producer only
 	double *sL = sF + NT * F * MM_Q;                               // [LOWK][MM_Q]   producer only
 	int32_t *sQi = reinterpret_cast<int32_t *>(sL + LOWK * MM_Q);  // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
+	double *sStage = reinterpret_cast<double *>(sQi + 2 * MM_Q);   // [MM_CONSUMERS][8][MM_STG_LD]  (ONE only) results on their way to TMA bulk stores
 	__shared__ __align__(8) uint64_t full_bar[MM_NS], empty_bar[MM_NS], item_bar[2];
 	__shared__ ItemGeom s_item[2];  // the producers locate the item's leaf (a binary search over tile offsets); the consumers read it here
 	if (threadIdx.x == 0) {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 		uint32_t g = 0;   // running step counter: stage = g % MM_NS, use count = g / MM_NS
 		uint32_t it = 0;  // running item counter: item buffer = it & 1
 		for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
-			const ItemGeom ig = item_geometry(item, tile0, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off);
+			const ItemGeom ig = item_geometry(item, tile0, n_tiles, L, n_dchunks, dg, offset, tile_off, m.fold_off, tile_leaf);
 			const int ib = it & 1;
 			// the consumers are done with this item buffer (two items ago); a fresh barrier passes the parity-1 wait
 			mbar_wait(&item_bar[ib], ((it >> 1) & 1u) ^ 1u);
@@ -308,7 +308,29 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				// ---- epilogue of a chunk: each output element is written exactly once; a fragment row is 2 consecutive doubles
 				const int32_t d0 = (ig.dc0 + dc) * MM_D;
 				const int32_t nd = min(MM_D, m.D - d0);
-				if (wide_out && nd == MM_D) {
+				if (MM_TMA_STORE && ONE && vec_out && nd == MM_D && !(dg & 0x2000)) {
+					// One stage per chunk means an epilogue per stage: hand the results to the TMA engine instead of issuing
+					// 16 global stores per thread.  Per 8-query block the warp parks its 8 x 32 fragment block in shared memory
+					// and lanes 0-7 each start one 256-byte bulk store of a row; the block is reused once those reads are done.
+					double *stg = sStage + warp * (8 * MM_STG_LD);
+#pragma unroll
+					for (int mi = 0; mi < 4; mi++) {
+						if (lane < 8) tma_bulk_wait_read0();
+						__syncwarp();
+#pragma unroll
+						for (int ni = 0; ni < 4; ni++) *reinterpret_cast<double2 *>(stg + fr * MM_STG_LD + ni * 8 + 2 * fc) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+						fence_async_smem();
+						__syncwarp();
+						if (lane < 8) {
+							const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + lane];
+							if (qi >= 0 && !(dg & 0x1000)) {
+								const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + lane - ring_base : (int64_t)qi;
+								tma_bulk_s2g(out + orow * out_stride + d0 + wd * 32, stg + lane * MM_STG_LD, 32 * 8);
+							}
+							tma_bulk_commit();
+						}
+					}
+				} else if (wide_out && nd == MM_D) {
 					// 256-bit stores of FULL 128-byte lines: a lane pair (fc, fc^1) swaps one 8x8 fragment row half so that each
 					// lane owns 4 consecutive components of one row; the 4 lanes of a row then cover 16 consecutive doubles
 					const bool odd = fc & 1;
@@ -357,7 +379,8 @@ namespace {
 size_t mma_smem_bytes(int N, int F, int lowk, bool one)
 {
 	const int ns = one ? MM_NS_ONE : MM_NS_MULTI, nw = one ? 2 : MM_NS_MULTI;
-	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64;
+	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64 +
+	       ((one && MM_TMA_STORE) ? (size_t)MM_CONSUMERS * 8 * MM_STG_LD * sizeof(double) : 0);
 }
 template <int NT, bool CUBIC, bool EXACT, bool ONE>
 void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, int64_t tile0, int64_t n_tiles,
@@ -368,7 +391,7 @@ void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_
 	const size_t smem = mma_smem_bytes(NT, CUBIC ? 4 : 2, 1 << ((CUBIC ? 2 : 1) * LOWD), ONE);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	LOCO_KERNEL("mesh_tensor_mma", st);
-	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, out, out_stride, n_dchunks, dg, tile0, n_tiles, ring_base);
+	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, w.tile_leaf, out, out_stride, n_dchunks, dg, tile0, n_tiles, ring_base);
 }
 template <int NT, bool CUBIC, bool EXACT>
 void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, int64_t tile0, int64_t n_tiles,
@@ -401,6 +424,7 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
 	if (const char *e = getenv("LOCO_MESH_DG")) dg = std::max(1, std::min(atoi(e), n_dchunks));  // tuning experiments
 	if (getenv("LOCO_MESH_NOSTORE")) dg |= 0x1000;
+	if (getenv("LOCO_MESH_NOTMASTORE")) dg |= 0x2000;
 	const int grid = sm_count * 2;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \

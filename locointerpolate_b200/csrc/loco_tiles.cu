@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(1024) scan_leaves_kernel(const int32_t *__rest
 	if (threadIdx.x == 0) { offset[L] = carry.x; tile_off[L] = carry.y; }
 }
 
+// leaf of every tile: tiles [tile_off[l], tile_off[l+1]) belong to leaf l
+__global__ void tile_leaf_kernel(const int32_t *__restrict__ tile_off, int32_t L, int32_t *__restrict__ tile_leaf)
+{
+	const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= L) return;
+	for (int32_t t = tile_off[l], t1 = tile_off[l + 1]; t < t1; t++) tile_leaf[t] = l;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 3. scatter queries (as cube coordinates) and their indices into the leaf buckets
 // ---------------------------------------------------------------------------------------------------
@@ -332,7 +340,7 @@ void eval_tiles(const DeviceModel &m, const double *q, double *out, const SortWo
 
 size_t sort_work_bytes(const DeviceModel &m, int64_t Q)
 {
-	const size_t ints = (size_t)m.L + (size_t)(m.L + 1) * 2 + (size_t)Q;
+	const size_t ints = (size_t)m.L + (size_t)(m.L + 1) * 2 + (size_t)Q + (size_t)(Q / 32 + m.L + 1);
 	return ((ints * sizeof(int32_t) + 127) & ~(size_t)127) + (size_t)Q * sorted_row_doubles(m.N) * sizeof(double) + 256;
 }
 
@@ -344,6 +352,7 @@ SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base)
 	w.offset = p; p += m.L + 1;
 	w.tile_off = p; p += m.L + 1;
 	w.rank = p; p += Q;
+	w.tile_leaf = p; p += Q / 32 + m.L + 1;
 	w.idx = nullptr;  // the index travels in the last slot of each sorted row
 	const size_t ints = (size_t)(p - reinterpret_cast<int32_t *>(base));
 	w.xs = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(base) + ((ints * sizeof(int32_t) + 127) & ~(size_t)127));
@@ -395,6 +404,7 @@ int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_
 	}
 	{ LOCO_KERNEL("scan_leaves", st);
 	scan_leaves_kernel<<<1, 1024, 0, st>>>(w.count, m.L, tile_q, w.offset, w.tile_off); }
+	tile_leaf_kernel<<<(unsigned)((m.L + 255) / 256), 256, 0, st>>>(w.tile_off, m.L, w.tile_leaf);
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 	case 1: scatter<1>(m, q, Q, leaf, status, w, st); break;
 	case 2: scatter<2>(m, q, Q, leaf, status, w, st); break;
