@@ -215,7 +215,7 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
 /* ---- tuning / accounting -------------------------------------------------------------------------------- */
 /* options: "lut" 1 locate grid before the k-d descent (default) | 0 descent from the root only;
  *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
- *                 4 L2-resident leaf-sorted chunks;  "chunk" queries per chunk of path 4 (0 = auto);
+ *                 4 L2-resident leaf-sorted chunks (exact counting sort) | 5 single-pass fixed-capacity leaf buckets (tensor leaves);  "chunk" queries per chunk of path 4 (0 = auto);
  *          "overlap" 1..4 (default 2): internal streams the chunks of path 4 are dealt over (forked from / joined to the caller's);
  *          "fp32" 1: optional fp32 mode of the throughput path for scalar functions on tensor-product leaves (path 0/4): point
  *                 location stays fp64 and bit-exact, basis polynomials and the weighted sum run in fp32 (1e-5 relative);

@@ -1,0 +1,232 @@
+// loco_bucket.cu -- single-pass leaf bucketing for scalar functions on tensor-product leaves (path 5).
+//
+// The exact counting sort of loco_sorted.cu reads every query twice (histogram, then scatter) because a bucket's
+// position is only known after the scan.  Here every leaf owns a FIXED-capacity bucket per chunk
+// (capacity = mean + 6 sigma of a uniform batch), so one pass suffices:
+//   1. bucket_scatter   map -> locate (locate grid) -> containment; leaf[] / status[]; slot = atomicAdd(count[leaf]);
+//                       slot < capacity: the 32-byte record {cube coordinates, query index} goes to bucket[leaf][slot];
+//                       otherwise the query index is appended to an overflow list
+//   2. bucket_eval      one WARP per leaf (persistent): the leaf's block (N*F centres, N reciprocals, F^N values) is copied
+//                       into the warp's shared-memory slot once, then the warp walks the bucket 32 records at a time --
+//                       coalesced record loads, broadcast shared-memory reads of leaf data, results to out[query index];
+//                       the warp clears the leaf's counter for the next chunk
+//   3. overflow_eval    the (normally empty) overflow list through the direct per-query evaluation
+// A skewed batch only moves queries from step 2 to step 3 (which then finds its leaf data hot in L1); results are
+// identical either way because every query is evaluated independently with the same arithmetic.
+#include <algorithm>
+#include <cmath>
+
+#include "loco_basis.cuh"
+#include "loco_device.h"
+
+namespace loco {
+
+namespace {
+
+__host__ __device__ constexpr int brec_doubles(int N) { return ((N * 8 + 4 + 31) / 32) * 4; }  // N coordinates + int32 index, whole sectors
+
+__device__ __forceinline__ void st_sector_cg(double *p, double a, double b, double c, double d)
+{
+	asm volatile("st.global.cg.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_sector_cg(const double *p, double &a, double &b, double &c, double &d)
+{
+	asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+constexpr int kItems = 2;  // queries per thread in the scatter pass
+
+template <int NT>
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
+                                                              uint8_t *__restrict__ status_out, double *__restrict__ out, int32_t *count, int32_t cap,
+                                                              double *__restrict__ rec, int32_t *ovf, int32_t *n_ovf)
+{
+	constexpr int RS = brec_doubles(NT);
+	const int64_t i0 = (int64_t)blockIdx.x * (256 * kItems) + threadIdx.x;
+	double p[kItems][NT];
+#pragma unroll
+	for (int k = 0; k < kItems; k++) {
+		const int64_t i = i0 + k * 256;
+		if (i < Q) {
+#pragma unroll
+			for (int d = 0; d < NT; d++) p[k][d] = __ldcs(q + i * NT + d);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < kItems; k++) {
+		const int64_t i = i0 + k * 256;
+		if (i >= Q) continue;
+		Coord<NT> x;
+		map_to_cube<NT>(m, p[k], x);
+		const int32_t leaf = descend<NT>(m, x);
+		const uint8_t st = located_status<NT>(m, x, leaf);
+		__stcs(leaf_out + i, leaf);
+		status_out[i] = st;
+		if (st != ST_OK) { out[i] = __longlong_as_double(0x7ff8000000000000LL); continue; }
+		const int32_t slot = atomicAdd(count + leaf, 1);
+		if (slot < cap) {
+			double v[RS];
+#pragma unroll
+			for (int d = 0; d < RS; d++) v[d] = d < NT ? x.get(d) : 0.0;
+			v[RS - 1] = __longlong_as_double((long long)(int32_t)i);
+			double *row = rec + ((int64_t)leaf * cap + slot) * RS;
+#pragma unroll
+			for (int d = 0; d < RS; d += 4) st_sector_cg(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
+		} else {
+			ovf[atomicAdd(n_ovf, 1)] = (int32_t)i;
+		}
+	}
+}
+
+// one warp per leaf; 8 warps per CTA, each with its own shared-memory copy of its current leaf block
+template <int NT, bool CUBIC, bool EXACT, bool FP32>
+__global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out)
+{
+	constexpr int RS = brec_doubles(NT);
+	extern __shared__ __align__(16) double s_blk[];  // [8][tl_stride]  (+ [8][K/2] doubles holding the fp32 values in fp32 mode)
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_warps = gridDim.x * 8;
+	const int blk_doubles = FP32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride;
+	double *blk = s_blk + (size_t)warp * ((blk_doubles + 1) & ~1);
+	for (int32_t leaf = blockIdx.x * 8 + warp; leaf < m.L; leaf += n_warps) {
+		const int32_t n = min(count[leaf], cap);
+		if (n == 0) continue;
+		__syncwarp();  // every lane is done with the previous leaf's block
+		if (lane == 0) count[leaf] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
+		// ---- the leaf's block into this warp's slot: 128-bit loads, all in flight together
+		{
+			const double2 *src = reinterpret_cast<const double2 *>(m.tl_block + (int64_t)leaf * m.tl_stride);
+			const int n2 = (FP32 ? m.tl_voff : m.tl_stride) / 2;
+			for (int e = lane; e < n2; e += 32) reinterpret_cast<double2 *>(blk)[e] = __ldg(src + e);
+			if (FP32) {
+				const float4 *vs = reinterpret_cast<const float4 *>(m.tl_vals_f32 + (int64_t)leaf * m.tensor_K);
+				float4 *dst = reinterpret_cast<float4 *>(blk + m.tl_voff);
+				for (int e = lane; e < m.tensor_K / 4; e += 32) dst[e] = __ldg(vs + e);
+			}
+		}
+		__syncwarp();
+		const double *bucket = rec + (int64_t)leaf * cap * RS;
+		// ---- 32 records at a time, the next group's records prefetched while this group is evaluated
+		double nv[RS];
+		if (lane < n) {
+#pragma unroll
+			for (int d = 0; d < RS; d += 4) ld_sector_cg(bucket + (int64_t)lane * RS + d, nv[d], nv[d + 1], nv[d + 2], nv[d + 3]);
+		}
+		for (int s = lane; s < n; s += 32) {
+			Coord<NT> x;
+#pragma unroll
+			for (int d = 0; d < NT; d++) x.set(d, nv[d]);
+			const int32_t qi = (int32_t)__double_as_longlong(nv[RS - 1]);
+			if (s + 32 < n) {
+#pragma unroll
+				for (int d = 0; d < RS; d += 4) ld_sector_cg(bucket + (int64_t)(s + 32) * RS + d, nv[d], nv[d + 1], nv[d + 2], nv[d + 3]);
+			}
+			double r;
+			if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
+			else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
+			out[qi] = r;
+		}
+	}
+}
+
+// the overflow list: queries whose bucket was full, evaluated one thread each straight from the global leaf blocks
+template <int NT, bool CUBIC, bool EXACT>
+__global__ void __launch_bounds__(256) overflow_eval_kernel(DeviceModel m, const double *__restrict__ q, const int32_t *__restrict__ leaf_in,
+                                                             const int32_t *__restrict__ ovf, int32_t *n_ovf, double *__restrict__ out)
+{
+	const int32_t n = *n_ovf;
+	for (int32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+		const int32_t i = ovf[e];
+		Coord<NT> x;
+		double p[NT];
+#pragma unroll
+		for (int d = 0; d < NT; d++) p[d] = q[(int64_t)i * NT + d];
+		map_to_cube<NT>(m, p, x);
+		out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf_in[i] * m.tl_stride, x);
+	}
+}
+__global__ void overflow_reset_kernel(int32_t *n_ovf) { *n_ovf = 0; }
+
+template <int NT, bool CUBIC, bool EXACT>
+void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w, int sm_count, bool fp32,
+               cudaStream_t st)
+{
+	{
+		LOCO_KERNEL("bucket_scatter", st);
+		bucket_scatter_kernel<NT><<<(unsigned)((Q + 256 * kItems - 1) / (256 * kItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count, w.cap, w.rec, w.ovf, w.n_ovf);
+	}
+	{
+		LOCO_KERNEL("bucket_eval", st);
+		const bool f32 = fp32 && m.tl_vals_f32 && (m.tensor_K % 4) == 0;
+		const int blk_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
+		const size_t smem = (size_t)8 * blk_doubles * sizeof(double);
+		const int grid = std::min(sm_count * 3, (m.L + 7) / 8);
+		if (f32) {
+			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, true>;
+			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out);
+		} else {
+			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, false>;
+			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out);
+		}
+	}
+	{
+		LOCO_KERNEL("overflow_eval", st);
+		overflow_eval_kernel<NT, CUBIC, EXACT><<<sm_count * 2, 256, 0, st>>>(m, q, leaf, w.ovf, w.n_ovf, out);
+		overflow_reset_kernel<<<1, 1, 0, st>>>(w.n_ovf);
+	}
+}
+
+} // namespace
+
+// bucket capacity for a chunk of `chunk` queries over L leaves: mean + 6 sigma of a uniform batch, a multiple of 32
+int bucket_capacity(const DeviceModel &m, int64_t chunk)
+{
+	const double mean = (double)chunk / (double)std::max(1, m.L);
+	const int cap = (int)std::ceil(mean + 6.0 * std::sqrt(mean) + 16.0);
+	return (cap + 31) & ~31;
+}
+bool bucket_path_supported(const DeviceModel &m) { return m.D == 1 && m.tensor_F > 0 && m.N >= 1 && m.N <= kMaxTemplateN && (size_t)m.tl_stride * 8 * 8 <= 160 * 1024; }
+
+size_t bucket_work_bytes(const DeviceModel &m, int64_t chunk)
+{
+	const size_t ints = (size_t)m.L + 4 + (size_t)chunk;
+	return ((ints * sizeof(int32_t) + 127) & ~(size_t)127) + (size_t)m.L * bucket_capacity(m, chunk) * brec_doubles(m.N) * sizeof(double) + 256;
+}
+BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base)
+{
+	BucketWork w;
+	int32_t *p = reinterpret_cast<int32_t *>(base);
+	w.count = p; p += m.L;
+	w.n_ovf = p; p += 4;
+	w.ovf = p; p += chunk;
+	const size_t ints = (size_t)(p - reinterpret_cast<int32_t *>(base));
+	w.rec = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(base) + ((ints * sizeof(int32_t) + 127) & ~(size_t)127));
+	w.cap = bucket_capacity(m, chunk);
+	return w;
+}
+int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t st)
+{
+	cudaMemsetAsync(w.count, 0, ((size_t)m.L + 4) * sizeof(int32_t), st);
+	return 0;
+}
+
+int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w,
+                                    int sm_count, bool fp32, cudaStream_t st)
+{
+	if (Q <= 0) return 0;
+	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
+#define LOCO_BCASE(NT)                                                                                                                   \
+	case NT:                                                                                                                             \
+		if (cubic) { if (exact) run_chunk<NT, true, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, st);                            \
+		             else run_chunk<NT, true, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, st); }                               \
+		else { if (exact) run_chunk<NT, false, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, st);                                 \
+		       else run_chunk<NT, false, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, st); }                                    \
+		break;
+	switch (m.N) { LOCO_BCASE(1) LOCO_BCASE(2) LOCO_BCASE(3) LOCO_BCASE(4) LOCO_BCASE(5) LOCO_BCASE(6) LOCO_BCASE(7) LOCO_BCASE(8) default: return 0; }
+#undef LOCO_BCASE
+	return 4;
+}
+
+} // namespace loco

@@ -328,7 +328,37 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool big = Q >= (int64_t)dm.L * 24 && Q >= (1 << 16) && leaf_bytes > 96 * 1024;
 		const bool sorted = !in_cube && (m->opt_path == 4 || (m->opt_path == 0 && big));
 		const bool tiles = !in_cube && m->opt_path == 2;
-		if (sorted) {
+		const bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256));
+		if (bucket) {
+			// single-pass fixed-capacity buckets: chunks of ~4M queries, at least 32 per leaf on average
+			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 32);
+			chunk = std::min(chunk, Q);
+			int rc;
+			if (!leaf) { if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)Q * sizeof(int32_t)))) return rc; leaf = (int32_t *)w.leaf; }
+			if (!status) { if ((rc = grow(m, &w.status, &w.status_b, (size_t)Q))) return rc; status = (uint8_t *)w.status; }
+			const int64_t n_chunks = (Q + chunk - 1) / chunk;
+			const int ns = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)4, m->opt_overlap, n_chunks}));
+			BucketWork bw[4];
+			cudaStream_t run_on[4] = {st, st, st, st};
+			for (int k = 0; k < ns; k++) {
+				void **buf = k == 0 ? &w.sorted : &w.sortedx[k - 1];
+				size_t *have = k == 0 ? &w.sorted_b : &w.sortedx_b[k - 1];
+				if ((rc = grow(m, buf, have, bucket_work_bytes(dm, chunk)))) return rc;
+				bw[k] = carve_bucket_work(dm, chunk, *buf);
+			}
+			if (ns > 1) {
+				CUDA_OK(m, cudaEventRecord(m->ev_fork, st));
+				for (int k = 0; k < ns; k++) { CUDA_OK(m, cudaStreamWaitEvent(m->aux[k], m->ev_fork, 0)); run_on[k] = m->aux[k]; }
+			}
+			for (int k = 0; k < ns; k++) launch_bucket_reset(dm, bw[k], run_on[k]);
+			int k = 0;
+			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
+				const int64_t n = std::min(chunk, Q - o);
+				m->launches += launch_eval_scalar_bucket_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, bw[k], m->sm_count, m->opt_fp32 != 0, run_on[k]);
+			}
+			if (ns > 1)
+				for (int j = 0; j < ns; j++) { CUDA_OK(m, cudaEventRecord(m->ev_join[j], m->aux[j])); CUDA_OK(m, cudaStreamWaitEvent(st, m->ev_join[j], 0)); }
+		} else if (sorted) {
 			// chunks sized so that records (32 B/query) + the out slice stay L2 resident; never fewer than ~16 queries per leaf
 			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 16);
 			chunk = std::min(chunk, Q);

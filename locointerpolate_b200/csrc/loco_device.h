@@ -178,4 +178,20 @@ int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t 
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
                                     int sm_count, bool fp32, cudaStream_t st);
 
+// ---- single-pass fixed-capacity leaf buckets (loco_bucket.cu)
+struct BucketWork {
+	int32_t *count;    // [L] queries that asked for a slot in the leaf's bucket (zero between chunks)
+	int32_t *n_ovf;    // number of overflow entries
+	int32_t *ovf;      // [chunk] query indices whose bucket was full
+	double *rec;       // [L * cap * record] records, bucket-major
+	int32_t cap;       // slots per bucket
+};
+int bucket_capacity(const DeviceModel &m, int64_t chunk);
+bool bucket_path_supported(const DeviceModel &m);
+size_t bucket_work_bytes(const DeviceModel &m, int64_t chunk);
+BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base);
+int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t st);
+int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w,
+                                    int sm_count, bool fp32, cudaStream_t st);
+
 } // namespace loco

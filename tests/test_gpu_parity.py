@@ -20,7 +20,7 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("path", [1, 2, 3, 4])
+@pytest.mark.parametrize("path", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_golden_vectors(golden, name, path):
     pb, z = golden(name)
@@ -216,7 +216,7 @@ def test_locate_grid_equals_descent_golden(golden, name):
     pb, z = golden(name)
     m = capi.Model.from_proto(pb, device=0)
     q = np.concatenate([z["q"], _adversarial_queries(m.N, 200_000, 3)])
-    for path in (1, 2, 4):
+    for path in (1, 2, 4, 5):
         m.set_option("path", path)
         m.set_option("chunk", 50_000)
         m.set_option("lut", 0)
@@ -332,3 +332,29 @@ def test_optional_fp32_mode(N, basis, level):
     diff = np.abs(res[0][0] - res[1][0])
     assert diff.max() > 0, "the fp32 mode did not run"
     assert (diff <= 1e-5 * np.maximum(np.abs(res[0][0]), 1.0)).all(), diff.max()
+
+
+def test_bucket_path_overflow_with_skewed_queries():
+    """path 5 (single-pass fixed-capacity leaf buckets): a batch concentrated in a few leaves overflows their buckets;
+    the overflow list must give exactly the results of the direct path."""
+    torch = _torch()
+    m = capi.Model.bootstrap(3, capi.CUBIC, 4, 1, True, fn=lambda p: 1 + np.sin(3 * p).sum(), device=0)
+    Q = 600_000
+    gen = torch.Generator("cuda").manual_seed(21)
+    tq = torch.rand((Q, 3), dtype=torch.float64, device="cuda", generator=gen)
+    tq[: Q // 2] = tq[: Q // 2] * 0.05 + 0.4     # half of the batch inside a 5 % cube (a handful of leaves)
+    tq[Q // 2: Q // 2 + 1000] = 1.5              # and some queries outside the domain
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for path in (1, 5):
+        m.set_option("path", path)
+        m.set_option("chunk", 200_000)
+        out = torch.empty(Q, dtype=torch.float64, device="cuda")
+        leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+        status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+        m.eval_device(tq.data_ptr(), Q, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+        torch.cuda.synchronize()
+        res[path] = (out.cpu().numpy(), leaf.cpu().numpy(), status.cpu().numpy())
+    assert np.array_equal(res[1][1], res[5][1]) and np.array_equal(res[1][2], res[5][2])
+    assert int((res[5][2] != 0).sum()) == 1000
+    assert np.array_equal(res[1][0], res[5][0], equal_nan=True)  # same arithmetic per query on both paths

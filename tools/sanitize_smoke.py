@@ -15,7 +15,7 @@ for name in ("cub2d_adapt6", "lin3d_adapt5", "cub3d_boot2"):
     m = capi.Model.from_proto(os.path.join(G, name + ".pb"), device=0)
     q = rng.random((3001, m.N)) * 1.02 - 0.01
     ref = None
-    for path in (1, 2, 3, 4):
+    for path in (1, 2, 3, 4, 5):
         m.set_option("path", path)
         m.set_option("chunk", 1000)
         out, leaf, status = m.eval(q)
