@@ -399,7 +399,7 @@ def measure(name, w, args, rank, world, local, config, full):
     for i in range(steps):
         step(i)
     prof = m.profile_end()
-    m.set_option("overlap", args.overlap or 2)
+    m.set_option("overlap", args.overlap or 3)
     tot_ms = sum(v["total_ms"] for v in prof.values()) or 1.0
     kernels = {k: {"launches_per_step": v["launches"] / steps, "ms_per_launch": v["total_ms"] / v["launches"], "share": v["total_ms"] / tot_ms}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}

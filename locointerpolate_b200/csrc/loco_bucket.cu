@@ -34,7 +34,7 @@ __device__ __forceinline__ void ld_sector_cg(const double *p, double &a, double 
 	asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-constexpr int kItems = 2;  // queries per thread in the scatter pass
+constexpr int kItems = 4;  // queries per thread in the scatter pass: independent load -> locate -> atomic -> store chains in flight
 
 template <int NT>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
@@ -80,8 +80,11 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 
 // one warp per leaf; 8 warps per CTA, each with its own shared-memory copy of its current leaf block
 template <int NT, bool CUBIC, bool EXACT, bool FP32>
-__global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out)
+__global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out,
+                                                              const double *__restrict__ q, const int32_t *__restrict__ leaf_in, const int32_t *__restrict__ ovf,
+                                                              const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next)
 {
+	if (blockIdx.x == 0 && threadIdx.x == 0) *n_ovf_next = 0;  // the counter of the NEXT chunk on this workspace (nobody reads it now)
 	constexpr int RS = brec_doubles(NT);
 	extern __shared__ __align__(16) double s_blk[];  // [8][tl_stride]  (+ [8][K/2] doubles holding the fp32 values in fp32 mode)
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,9 +130,20 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 			out[qi] = r;
 		}
 	}
+	// ---- the overflow list (queries whose bucket was full; normally empty): one thread each, straight from the global leaf blocks
+	const int32_t n_over = *n_ovf;
+	for (int32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_over; e += gridDim.x * blockDim.x) {
+		const int32_t i = ovf[e];
+		Coord<NT> x;
+		double p[NT];
+#pragma unroll
+		for (int d = 0; d < NT; d++) p[d] = q[(int64_t)i * NT + d];
+		map_to_cube<NT>(m, p, x);
+		out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf_in[i] * m.tl_stride, x);
+	}
 }
 
-// the overflow list: queries whose bucket was full, evaluated one thread each straight from the global leaf blocks
+// (kept for reference) the overflow list as a kernel of its own
 template <int NT, bool CUBIC, bool EXACT>
 __global__ void __launch_bounds__(256) overflow_eval_kernel(DeviceModel m, const double *__restrict__ q, const int32_t *__restrict__ leaf_in,
                                                              const int32_t *__restrict__ ovf, int32_t *n_ovf, double *__restrict__ out)
@@ -149,11 +163,13 @@ __global__ void overflow_reset_kernel(int32_t *n_ovf) { *n_ovf = 0; }
 
 template <int NT, bool CUBIC, bool EXACT>
 void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w, int sm_count, bool fp32,
-               cudaStream_t st)
+               int parity, cudaStream_t st)
 {
+	// overflow counters alternate between the chunks of a workspace: the evaluation of chunk j clears the counter of chunk j+1
+	int32_t *n_ovf = w.n_ovf + (parity & 1), *n_ovf_next = w.n_ovf + ((parity + 1) & 1);
 	{
 		LOCO_KERNEL("bucket_scatter", st);
-		bucket_scatter_kernel<NT><<<(unsigned)((Q + 256 * kItems - 1) / (256 * kItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count, w.cap, w.rec, w.ovf, w.n_ovf);
+		bucket_scatter_kernel<NT><<<(unsigned)((Q + 256 * kItems - 1) / (256 * kItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count, w.cap, w.rec, w.ovf, n_ovf);
 	}
 	{
 		LOCO_KERNEL("bucket_eval", st);
@@ -164,17 +180,12 @@ void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, in
 		if (f32) {
 			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, true>;
 			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next);
 		} else {
 			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, false>;
 			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next);
 		}
-	}
-	{
-		LOCO_KERNEL("overflow_eval", st);
-		overflow_eval_kernel<NT, CUBIC, EXACT><<<sm_count * 2, 256, 0, st>>>(m, q, leaf, w.ovf, w.n_ovf, out);
-		overflow_reset_kernel<<<1, 1, 0, st>>>(w.n_ovf);
 	}
 }
 
@@ -213,20 +224,20 @@ int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t 
 }
 
 int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w,
-                                    int sm_count, bool fp32, cudaStream_t st)
+                                    int sm_count, bool fp32, int parity, cudaStream_t st)
 {
 	if (Q <= 0) return 0;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_BCASE(NT)                                                                                                                   \
 	case NT:                                                                                                                             \
-		if (cubic) { if (exact) run_chunk<NT, true, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, st);                            \
-		             else run_chunk<NT, true, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, st); }                               \
-		else { if (exact) run_chunk<NT, false, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, st);                                 \
-		       else run_chunk<NT, false, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, st); }                                    \
+		if (cubic) { if (exact) run_chunk<NT, true, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st);                            \
+		             else run_chunk<NT, true, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st); }                               \
+		else { if (exact) run_chunk<NT, false, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st);                                 \
+		       else run_chunk<NT, false, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st); }                                    \
 		break;
 	switch (m.N) { LOCO_BCASE(1) LOCO_BCASE(2) LOCO_BCASE(3) LOCO_BCASE(4) LOCO_BCASE(5) LOCO_BCASE(6) LOCO_BCASE(7) LOCO_BCASE(8) default: return 0; }
 #undef LOCO_BCASE
-	return 4;
+	return 2;
 }
 
 } // namespace loco

@@ -71,7 +71,7 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 2, opt_uniform = 1;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
@@ -351,10 +351,11 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 				for (int k = 0; k < ns; k++) { CUDA_OK(m, cudaStreamWaitEvent(m->aux[k], m->ev_fork, 0)); run_on[k] = m->aux[k]; }
 			}
 			for (int k = 0; k < ns; k++) launch_bucket_reset(dm, bw[k], run_on[k]);
-			int k = 0;
+			int k = 0, used[4] = {0, 0, 0, 0};
 			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
 				const int64_t n = std::min(chunk, Q - o);
-				m->launches += launch_eval_scalar_bucket_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, bw[k], m->sm_count, m->opt_fp32 != 0, run_on[k]);
+				m->launches += launch_eval_scalar_bucket_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, bw[k], m->sm_count, m->opt_fp32 != 0, used[k]++,
+				                                               run_on[k]);
 			}
 			if (ns > 1)
 				for (int j = 0; j < ns; j++) { CUDA_OK(m, cudaEventRecord(m->ev_join[j], m->aux[j])); CUDA_OK(m, cudaStreamWaitEvent(st, m->ev_join[j], 0)); }
