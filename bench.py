@@ -251,7 +251,7 @@ def main():
 
 KERNEL_ROLE = {  # which part of SURVEY.md 8(d)'s per-query byte formula a kernel covers
     "sorted_count": "locate", "locate_count": "locate", "sorted_scatter": "sort", "scatter": "sort", "sorted_scan": "sort", "scan_leaves": "sort",
-    "sorted_eval": "eval", "eval_tensor_tiles": "eval", "eval_tiles": "eval", "mesh_tensor_mma": "eval", "mesh_tensor_tiles": "eval",
+    "bucket_scatter": "locate+sort", "bucket_eval": "eval", "sorted_eval": "eval", "eval_tensor_tiles": "eval", "eval_tiles": "eval", "mesh_tensor_mma": "eval", "mesh_tensor_tiles": "eval",
     "mesh_gather": "eval", "weights": "eval", "eval_scalar_direct": "all", "eval_tensor_direct": "all", "jitter_points": "generate",
     "error_reduce": "reduce", "mesh_nan_rows": "other", "checksum": "other",
 }
@@ -260,7 +260,7 @@ KERNEL_ROLE = {  # which part of SURVEY.md 8(d)'s per-query byte formula a kerne
 def role_bytes_per_query(role, N, depth, T, K, D):
     locate = 8 * N + 16 * depth + 5
     evalb = T * (16 * N + 8 + 4) + K * D * 8 + 8 * D
-    return {"locate": locate, "sort": 2 * (8 * N + 8), "eval": evalb + 8 * N, "all": locate + evalb, "generate": 8 * N + 12, "reduce": 8 * D * 2 + 5}.get(role, 0)
+    return {"locate": locate, "sort": 2 * (8 * N + 8), "locate+sort": locate + 2 * (8 * N + 8), "eval": evalb + 8 * N, "all": locate + evalb, "generate": 8 * N + 12, "reduce": 8 * D * 2 + 5}.get(role, 0)
 
 
 def measure(name, w, args, rank, world, local, config, full):

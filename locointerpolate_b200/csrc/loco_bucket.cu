@@ -10,7 +10,7 @@
 //                       into the warp's shared-memory slot once, then the warp walks the bucket 32 records at a time --
 //                       coalesced record loads, broadcast shared-memory reads of leaf data, results to out[query index];
 //                       the warp clears the leaf's counter for the next chunk
-//   3. overflow_eval    the (normally empty) overflow list through the direct per-query evaluation
+//   3.                  at the end of the same kernel the (normally empty) overflow list goes through the direct per-query evaluation
 // A skewed batch only moves queries from step 2 to step 3 (which then finds its leaf data hot in L1); results are
 // identical either way because every query is evaluated independently with the same arithmetic.
 #include <algorithm>
