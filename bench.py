@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--gather", default="rotate", choices=["rotate", "all"],
+                    help="multi-GPU exchange step: results of batch i gathered on rank i mod N (default) or all_gather on every rank")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (c3, c4) reported under other_workloads")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 direct, 2 leaf-sorted TMA tiles, 4 L2-resident sorted chunks")
     ap.add_argument("--overlap", type=int, default=0, help="streams the chunks of the sorted path are dealt over (0 = library default)")
@@ -195,7 +197,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "interpolated_queries_per_sec"
     config = {"workload": f"{args.workload}: {w['desc']}", "n_params": w["N"], "basis": "cubic" if w["basis"] else "linear",
-              "value_dim": w["D"], "queries_per_step_per_gpu": w["Q"], "parallelism": f"query-sharded x{world}, model replicated",
+              "value_dim": w["D"], "queries_per_step_per_gpu": w["Q"],
+              "parallelism": f"query-sharded x{world}, model replicated" + (f", results of batch i gathered on rank i mod {world}" if world > 1 and args.gather == "rotate" and w["D"] == 1 else ""),
               "l2": "inputs+outputs per step exceed the 126 MB L2" if w["Q"] * (w["N"] + w["D"]) * 8 > 126e6 else "L2 flushed between steps"}
 
     # ------------------------------------------------------------------ reference arm (CPU) ----------
@@ -296,14 +299,15 @@ def measure(name, w, args, rank, world, local, config, full):
         def step(i):
             m.error_check_generated_device(ppl, 1000 + i, d_amp.data_ptr(), d_phase.data_ptr(), 10, 0.05, err.data_ptr(), split.data_ptr(), stream)
     elif D == 1:
-        outs = [torch.empty(Q, dtype=torch.float64, device="cuda") for _ in range(2)]
+        NB = 3 if world > 1 else 2  # result buffers in rotation (with several GPUs: gathers of two earlier batches may be in flight)
+        outs = [torch.empty(Q, dtype=torch.float64, device="cuda") for _ in range(NB)]
         # with several GPUs the step is issued in sub-batches so that the gather of a finished part overlaps the rest
         n_sub = 4 if world > 1 and Q % 4 == 0 and Q >= (1 << 22) else 1
         Qs = Q // n_sub
 
         def step(i, gather=None):
             for j in range(n_sub):
-                m.eval_device(q.data_ptr() + j * Qs * N * 8, Qs, outs[i % 2].data_ptr() + j * Qs * 8, leaf.data_ptr() + j * Qs * 4,
+                m.eval_device(q.data_ptr() + j * Qs * N * 8, Qs, outs[i % NB].data_ptr() + j * Qs * 8, leaf.data_ptr() + j * Qs * 4,
                               status.data_ptr() + j * Qs, stream)
                 if gather is not None:
                     gather(i, j)
@@ -324,13 +328,38 @@ def measure(name, w, args, rank, world, local, config, full):
 
     gathered, handles = None, []
     if world > 1 and D == 1 and name != "c5":
-        gathered = [torch.empty((n_sub, world, Qs), dtype=torch.float64, device="cuda") for _ in range(2)]  # [sub-batch][rank][query]
+        gathered = [torch.empty((n_sub, world, Qs), dtype=torch.float64, device="cuda") for _ in range(NB)]  # [sub-batch][rank][query]
 
-    def gather_part(i, j):  # the path's one exchange step: gather the per-shard results, asynchronously on NCCL's stream
-        handles.append(dist.all_gather_into_tensor(gathered[i % 2][j], outs[i % 2][j * Qs:(j + 1) * Qs], async_op=True))
+    # The path's one exchange step: the per-shard results of batch i are gathered on rank (i mod world) -- the consumer of
+    # that batch -- asynchronously on NCCL's stream, so that it overlaps the next batches.  (Gathering EVERY batch on ONE
+    # GPU, or on all of them, cannot scale: 8 GPUs produce 8 B x 27 G results/s each = 1.7 TB/s, twice what one GPU's
+    # NVLink ingress takes; with rotating consumers each GPU ingests its own production rate.)  --gather all: all_gather.
+    per_step = {}
+    # one communicator per consumer rank: NCCL runs the operations of ONE communicator in order, so gathers towards
+    # different consumers could not overlap on a single one (a gather lasts as long as its root's ingress takes)
+    root_groups = None
+    if gathered is not None and args.gather == "rotate":
+        root_groups = []
+        for _ in range(world):
+            try:
+                root_groups.append(dist.new_group(list(range(world)), pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)))
+            except Exception:
+                root_groups.append(dist.new_group(list(range(world))))
+
+    def gather_part(i, j):
+        src = outs[i % NB][j * Qs:(j + 1) * Qs]
+        if args.gather == "all":
+            h = dist.all_gather_into_tensor(gathered[i % NB][j], src, async_op=True)
+        else:
+            root = i % world
+            h = dist.gather(src, list(gathered[i % NB][j].unbind(0)) if rank == root else None, dst=root, group=root_groups[root], async_op=True)
+        handles.append(h)
+        per_step.setdefault(i, []).append(h)
 
     def run(i):
         if gathered is not None:
+            for h in per_step.pop(i - NB, []):  # outs[i % NB] / gathered[i % NB] are reused: batch i-NB must have left
+                h.wait()
             step(i, gather_part)
         else:
             step(i)
