@@ -64,8 +64,8 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, i
 	g.leaf = lo;
 	g.qbeg = __ldg(offset + lo) + (int32_t)(tile - __ldg(tile_off + lo)) * MM_Q;
 	g.nq = min(MM_Q, __ldg(offset + lo + 1) - g.qbeg);
-	g.dc0 = (int32_t)dgroup * (dg & 0xfff);
-	g.n_dc = min(dg & 0xfff, n_dchunks - g.dc0);
+	g.dc0 = (int32_t)dgroup * dg;
+	g.n_dc = min(dg, n_dchunks - g.dc0);
 	g.row0 = __ldg(fold_off + lo);
 	g.K = __ldg(fold_off + lo + 1) - g.row0;
 	return g;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	// `out` (a ring the caller consumes in leaf order) instead of row (query index)
 	const int32_t L = m.L;
 	const int64_t n_tiles = n_tiles_arg >= 0 ? n_tiles_arg : (int64_t)tile_off[L];
-	const int32_t n_dgroups = (n_dchunks + (dg & 0xfff) - 1) / (dg & 0xfff);
+	const int32_t n_dgroups = (n_dchunks + dg - 1) / dg;
 	const int64_t total = n_tiles * n_dgroups;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				// ---- epilogue of a chunk: each output element is written exactly once; a fragment row is 2 consecutive doubles
 				const int32_t d0 = (ig.dc0 + dc) * MM_D;
 				const int32_t nd = min(MM_D, m.D - d0);
-				if (MM_TMA_STORE && ONE && vec_out && nd == MM_D && !(dg & 0x2000)) {
+				if (MM_TMA_STORE && ONE && vec_out && nd == MM_D) {
 					// One stage per chunk means an epilogue per stage: hand the results to the TMA engine instead of issuing
 					// 16 global stores per thread.  Per 8-query block the warp parks its 8 x 32 fragment block in shared memory
 					// and lanes 0-7 each start one 256-byte bulk store of a row; the block is reused once those reads are done.
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 						__syncwarp();
 						if (lane < 8) {
 							const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + lane];
-							if (qi >= 0 && !(dg & 0x1000)) {
+							if (qi >= 0) {
 								const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + lane - ring_base : (int64_t)qi;
 								tma_bulk_s2g(out + orow * out_stride + d0 + wd * 32, stg + lane * MM_STG_LD, 32 * 8);
 							}
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 							const int n0 = 2 * p, n1 = 2 * p + 1;
 							const double s0 = odd ? acc[mi][n0][0] : acc[mi][n1][0], s1 = odd ? acc[mi][n0][1] : acc[mi][n1][1];
 							const double r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-							if (qi < 0 || (dg & 0x1000)) continue;
+							if (qi < 0) continue;
 							if (odd) st_stream_f64x4(o + n1 * 8 + 2 * (fc - 1), r0, r1, acc[mi][n1][0], acc[mi][n1][1]);
 							else st_stream_f64x4(o + n0 * 8 + 2 * fc, acc[mi][n0][0], acc[mi][n0][1], r0, r1);
 						}
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 #pragma unroll
 				for (int mi = 0; mi < 4; mi++) {
 					const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
-					if (qi < 0 || (dg & 0x1000)) continue;  // EXPERIMENT: bit 12 of dg disables the result stores
+					if (qi < 0) continue;
 					const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
 					double *o = out + orow * out_stride + d0;
 #pragma unroll
@@ -422,9 +422,6 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	int dg = std::max(4, (32 + n_stages - 1) / n_stages);
 	const int64_t slice_cap = ((int64_t)28 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
 	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
-	if (const char *e = getenv("LOCO_MESH_DG")) dg = std::max(1, std::min(atoi(e), n_dchunks));  // tuning experiments
-	if (getenv("LOCO_MESH_NOSTORE")) dg |= 0x1000;
-	if (getenv("LOCO_MESH_NOTMASTORE")) dg |= 0x2000;
 	const int grid = sm_count * 2;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \
