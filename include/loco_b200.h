@@ -93,6 +93,8 @@ typedef struct loco_info {
 	int64_t n_samples, n_value_rows, n_leaves, n_cells, n_border_cells, n_basis_functions;
 	int64_t n_support_entries, n_terms, device_bytes;
 	int64_t n_fold_entries;  /* value rows over all tensor leaves after folding samples that share a value object (0: no tensor leaves) */
+	int64_t n_eval_cells;    /* evaluation cells of the sorted scalar path (0: sorted by leaf) */
+	int64_t n_eval_terms;    /* term-list entries over all evaluation cells */
 } loco_info_t;
 
 /* f : original parameter space [N] -> value [D]   (LCFunction::evalShapeInfo, LCFunction/LCFunction.h:32) */
@@ -220,7 +222,9 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
  *          "fp32" 1: optional fp32 mode of the throughput path for scalar functions on tensor-product leaves (path 0/4): point
  *                 location stays fp64 and bit-exact, basis polynomials and the weighted sum run in fp32 (1e-5 relative);
  *          "uniform" 1 (default): cubic tensor leaves with equally spaced centres form their four factors per dimension from one parameter;
- *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0) */
+ *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0);
+ *          "ecells" 1 (default): path 4 on generic leaves sorts by evaluation cell (a regular sub-grid of the leaves with many terms,
+ *                 each cell listing only the basis functions that reach it) | 0 by leaf */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);

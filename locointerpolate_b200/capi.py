@@ -44,7 +44,7 @@ class _GraphStruct(C.Structure):
 class _Info(C.Structure):
     _fields_ = [(n, _i32) for n in ("n_params", "value_dim", "basis_type", "exact_rcp", "depth", "max_support", "max_terms", "device")] + \
                [(n, _i64) for n in ("n_samples", "n_value_rows", "n_leaves", "n_cells", "n_border_cells", "n_basis_functions",
-                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries")]
+                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries", "n_eval_cells", "n_eval_terms")]
 
 
 VALUE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp)

@@ -64,6 +64,8 @@ struct loco_model {
 	double *d_values = nullptr;
 	double *d_term_wv = nullptr;
 	double *d_mterm_wv = nullptr;
+	double *d_eterm_wv = nullptr;
+	const int32_t *d_ecell_off = nullptr;
 	double *d_tl_block = nullptr;
 	float *d_tl_vals_f32 = nullptr;
 	int64_t n_terms = 0;
@@ -138,6 +140,7 @@ int refresh_term_wv(loco_model *m)
 	if (m->dm.D == 1) {
 		m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
 		m->launches += launch_update_mterm_wv(m->dm, m->d_mterm_wv, nullptr);
+		m->launches += launch_update_eterm_wv(m->dm, m->d_eterm_wv, nullptr);
 		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, m->d_tl_vals_f32, nullptr);
 	}
 	CUDA_OK(m, cudaGetLastError());
@@ -202,6 +205,25 @@ int build_device_model(loco_model *m)
 		dm.mterm_wv = dwv;
 		std::vector<double>().swap(f.mterm_cs);
 		std::vector<int32_t>().swap(f.mrun_term);
+	}
+	dm.ecell_off = nullptr; dm.eterm_src = nullptr; dm.eterm_wv = nullptr; dm.n_ecells = 0; dm.n_eterms = 0;
+	if (!f.ecell_off.empty() && dm.mterm_off) {
+		std::vector<int32_t> coff = narrow(m, f.ecell_off, &ok), toff = narrow(m, f.eterm_off, &ok);
+		if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
+		dm.n_ecells = (int32_t)f.ecell_off.back();
+		dm.n_eterms = f.eterm_off.back();
+		if ((rc = upload(m, coff, &dm.ecell_off))) return rc;
+		if ((rc = upload(m, f.ecell_bits, &dm.ecell_bits))) return rc;
+		if ((rc = upload(m, toff, &dm.eterm_off))) return rc;
+		if ((rc = upload(m, f.eterm_cs, &dm.eterm_cs, 2))) return rc;
+		if ((rc = upload(m, f.eterm_src, &dm.eterm_src))) return rc;
+		std::vector<double> zeros((size_t)dm.n_eterms + 2, 0.0);
+		const double *dwv = nullptr;
+		if ((rc = upload(m, zeros, &dwv))) return rc;
+		m->d_eterm_wv = const_cast<double *>(dwv);
+		dm.eterm_wv = dwv;
+		std::vector<double>().swap(f.eterm_cs);
+		std::vector<int32_t>().swap(f.eterm_src);
 	}
 	std::vector<int32_t> dterm_off = narrow(m, f.dterm_off, &ok);
 	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
@@ -361,7 +383,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 				for (int j = 0; j < ns; j++) { CUDA_OK(m, cudaEventRecord(m->ev_join[j], m->aux[j])); CUDA_OK(m, cudaStreamWaitEvent(st, m->ev_join[j], 0)); }
 		} else if (sorted) {
 			// chunks sized so that records (32 B/query) + the out slice stay L2 resident; never fewer than ~16 queries per leaf
-			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 16);
+			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)(dm.ecell_off ? dm.n_ecells : dm.L) * 16);
 			chunk = std::min(chunk, Q);
 			int rc;
 			if ((rc = grow(m, &w.sorted, &w.sorted_b, sorted_work_bytes(dm, chunk)))) return rc;
@@ -599,6 +621,8 @@ int loco_model_info(const loco_model_t *m, loco_info_t *info)
 	info->n_terms = f.term_off.back();
 	info->device_bytes = m->device_bytes;
 	info->n_fold_entries = f.fold_off.empty() ? 0 : f.fold_off.back();
+	info->n_eval_cells = f.ecell_off.empty() ? 0 : f.ecell_off.back();
+	info->n_eval_terms = f.eterm_off.empty() ? 0 : f.eterm_off.back();
 	return LOCO_OK;
 }
 
@@ -947,6 +971,11 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "uniform")) { m->opt_uniform = value; m->dm.tensor_uniform = (m->flat.tensor_uniform && value) ? 1 : 0; return LOCO_OK; }  // 0: four separate factor evaluations
 	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
+	if (!strcmp(name, "ecells")) {  // 0: sorted path keyed by leaf, 1: by evaluation cell where the model has them (default)
+		if (m->dm.ecell_off) m->d_ecell_off = m->dm.ecell_off;
+		m->dm.ecell_off = value ? m->d_ecell_off : nullptr;
+		return LOCO_OK;
+	}
 	if (!strcmp(name, "lut")) {  // 0: plain k-d descent from the root, 1: locate grid first (default)
 		if (m->dm.lut) m->d_lut = m->dm.lut;
 		m->opt_lut = value;

@@ -38,6 +38,14 @@ struct DeviceModel {
 	const double *mterm_cs, *mterm_wv;
 	const int32_t *mrun_off, *mrun_term;
 	int64_t n_mterms;
+	// evaluation cells (Flat::ecell_*; ecell_off == nullptr: not built).  eterm_wv[t] = mterm_wv[eterm_src[t]].
+	const int32_t *ecell_off;
+	const uint8_t *ecell_bits;
+	const int32_t *eterm_off;
+	const double *eterm_cs, *eterm_wv;
+	const int32_t *eterm_src;
+	int32_t n_ecells;
+	int64_t n_eterms;
 	// derivative-only extra terms of the linear basis (CSR by leaf; see Flat::dterm_*)
 	const int32_t *dterm_off;
 	const double *dterm_cs, *dterm_w;
@@ -139,6 +147,7 @@ size_t sort_work_bytes(const DeviceModel &m, int64_t Q);
 SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
 int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t st);
+int launch_update_eterm_wv(const DeviceModel &m, double *eterm_wv, cudaStream_t st);
 int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);

@@ -74,6 +74,18 @@ struct Flat {
 	std::vector<int64_t> mrun_off;     // [M+1] CSR: the original terms merged into each
 	std::vector<int32_t> mrun_term;    // [sum T] indices into the term arrays above
 
+	// evaluation cells (scalar functions on generic leaves): in the reference's adaptive trees most basis functions that
+	// overlap a leaf are much NARROWER than the leaf (refineCell refines in all directions), so at any one point only a
+	// fraction of the leaf's terms is non-zero.  Leaves with many merged terms are cut into a regular grid of
+	// 2^bits[d] cells per dimension; every cell lists the merged terms whose box reaches it (with a margin that covers
+	// the +-1e-6 acceptance band and the rounding of the cell index, so the choice of cell never changes a result).
+	// The throughput path sorts queries by evaluation cell instead of by leaf.
+	std::vector<int64_t> ecell_off;    // [L+1] first evaluation cell of each leaf
+	std::vector<uint8_t> ecell_bits;   // [L * N]
+	std::vector<int64_t> eterm_off;    // [E+1] CSR by evaluation cell
+	std::vector<double> eterm_cs;      // [sum * 2N]
+	std::vector<int32_t> eterm_src;    // [sum] index of the merged term (for weight * value)
+
 	// derivative-only extra terms (linear basis; see loco_flatten.cpp): hats outside the leaf that the reference's
 	// LCLinearBSpline::evalDeriv still counts because it compares the SIGNED distance with 1
 	std::vector<int64_t> dterm_off;    // [L+1]

@@ -309,6 +309,81 @@ Status flatten(const Graph &g, Flat *out)
 		if (T >= (int64_t)0x7fffffff || M * 4 > T * 3) {  // not worth a second copy of the term list
 			f.mterm_off.clear(); f.mterm_cs.clear(); f.mrun_off.clear(); f.mrun_term.clear();
 		}
+		// ---- evaluation cells (see loco_flat.h): only where a leaf carries many merged terms
+		if (!f.mterm_off.empty()) {
+			// cells of about a quarter of the narrowest support, up to 32 per dimension and 1,024 per leaf; coarser if the
+			// lists would outgrow 32x the merged list (or 1 GB)
+			const int kMinTerms = 24, kMaxBitsPerDim = 5, kMaxBits = 10;
+			const int64_t kMaxEterms = std::min<int64_t>(((int64_t)1 << 30) / ((2 * N + 2) * 8), 32 * f.mterm_off.back());
+			bool any = false, ok = false;
+			for (double kCellScale = 0.25; kCellScale <= 2.0 && !ok; kCellScale *= 2.0) {
+			ok = true; any = false;
+			f.eterm_cs.clear(); f.eterm_src.clear();
+			f.ecell_off.assign(1, 0);
+			f.ecell_bits.assign((size_t)L * N, 0);
+			f.eterm_off.assign(1, 0);
+			std::vector<double> smin((size_t)N);
+			for (int64_t l = 0; l < L && ok; l++) {
+				const int64_t m0 = f.mterm_off[(size_t)l], m1 = f.mterm_off[(size_t)l + 1];
+				const double *lo = &f.leaf_lo[(size_t)l * N], *hi = &f.leaf_hi[(size_t)l * N];
+				uint8_t *bits = &f.ecell_bits[(size_t)l * N];
+				if (m1 - m0 >= kMinTerms) {
+					for (int i = 0; i < N; i++) smin[(size_t)i] = 1e300;
+					for (int64_t t = m0; t < m1; t++)
+						for (int i = 0; i < N; i++) {
+							const double v = f.mterm_cs[(size_t)t * 2 * N + 2 * i + 1];
+							smin[(size_t)i] = std::min(smin[(size_t)i], f.exact_rcp ? 1.0 / v : v);
+						}
+					int total = 0;
+					for (int i = 0; i < N; i++) {
+						const double cells = (hi[i] - lo[i]) / (kCellScale * smin[(size_t)i]);  // cell ~ full width of the narrowest function
+						int b = 0;
+						while (b < kMaxBitsPerDim && (double)(2 << b) <= cells) b++;
+						bits[i] = (uint8_t)b;
+						total += b;
+					}
+					while (total > kMaxBits) {  // trim the finest dimension first
+						int best = 0;
+						for (int i = 1; i < N; i++) if (bits[i] > bits[best]) best = i;
+						bits[best]--; total--;
+					}
+					any = any || total > 0;
+				}
+				int64_t n_cells = 1;
+				for (int i = 0; i < N; i++) n_cells <<= bits[i];
+				std::vector<double> clo((size_t)N), chi((size_t)N);
+				for (int64_t c = 0; c < n_cells; c++) {
+					int64_t r = c;
+					for (int i = 0; i < N; i++) {
+						const int64_t g = (int64_t)1 << bits[i], k = r % g;
+						r /= g;
+						const double h = (hi[i] - lo[i]) / (double)g;
+						// margin: the acceptance band (1e-6), the rounding of the cell index, and a relative guard
+						const double mg = 2.5e-6 + 1e-9 * (std::fabs(lo[i]) + std::fabs(hi[i])) + 1e-6 * h;
+						clo[(size_t)i] = lo[i] + h * (double)k - mg;
+						chi[(size_t)i] = lo[i] + h * (double)(k + 1) + mg;
+					}
+					for (int64_t t = m0; t < m1; t++) {
+						bool reach = true;
+						for (int i = 0; i < N && reach; i++) {
+							const double cc = f.mterm_cs[(size_t)t * 2 * N + 2 * i], v = f.mterm_cs[(size_t)t * 2 * N + 2 * i + 1];
+							const double sp = f.exact_rcp ? 1.0 / v : v;
+							if (cc + sp < clo[(size_t)i] || cc - sp > chi[(size_t)i]) reach = false;
+						}
+						if (!reach) continue;
+						f.eterm_cs.insert(f.eterm_cs.end(), f.mterm_cs.begin() + t * 2 * N, f.mterm_cs.begin() + (t + 1) * 2 * N);
+						f.eterm_src.push_back((int32_t)t);
+					}
+					f.eterm_off.push_back((int64_t)f.eterm_src.size());
+					if ((int64_t)f.eterm_src.size() > kMaxEterms) { ok = false; break; }
+				}
+				f.ecell_off.push_back(f.ecell_off.back() + n_cells);
+			}
+			}
+			if (!any || !ok || f.ecell_off.back() >= (int64_t)0x7fffffff) {
+				f.ecell_off.clear(); f.ecell_bits.clear(); f.eterm_off.clear(); f.eterm_cs.clear(); f.eterm_src.clear();
+			}
+		}
 	}
 
 	// ---- tensor-product structure (see loco_flat.h) ---------------------------------------------------

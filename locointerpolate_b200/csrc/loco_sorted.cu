@@ -39,6 +39,33 @@ __device__ __forceinline__ void ld_sector_cg(const double *p, double &a, double 
 	asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+// number of sort buckets: evaluation cells where the model has them (Flat::ecell_*), leaves otherwise
+__host__ __device__ __forceinline__ int32_t sort_buckets(const DeviceModel &m) { return m.ecell_off ? m.n_ecells : m.L; }
+
+// evaluation cell of a located point.  Pure function of (x, leaf): the count and the scatter pass get the same cell.
+// The index need not be exact at cell faces — neighbouring cells both list every term that reaches the face.
+template <int NT>
+__device__ __forceinline__ int32_t eval_cell(const DeviceModel &m, const Coord<NT> &x, int32_t leaf)
+{
+	if (!m.ecell_off) return leaf;
+	const int N = NT > 0 ? NT : m.N;
+	int idx = 0, shift = 0;
+#pragma unroll
+	for (int d = 0; d < (NT > 0 ? NT : kMaxN); d++) {
+		if (d >= N) break;
+		const int b = m.ecell_bits[(int64_t)leaf * N + d];
+		if (b) {
+			const double lo = m.leaf_lo[(int64_t)leaf * N + d], hi = m.leaf_hi[(int64_t)leaf * N + d];
+			const int g = 1 << b;
+			int k = (int)((x.get(d) - lo) * (double)g / (hi - lo));
+			k = max(0, min(g - 1, k));
+			idx |= k << shift;
+			shift += b;
+		}
+	}
+	return __ldg(m.ecell_off + leaf) + idx;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 1. locate + histogram
 // ---------------------------------------------------------------------------------------------------
@@ -68,7 +95,7 @@ __global__ void __launch_bounds__(256) sorted_count_kernel(DeviceModel m, const 
 		const uint8_t st = located_status<NT>(m, x, leaf);
 		leaf_out[i] = leaf;
 		status_out[i] = st;
-		if (st == ST_OK) atomicAdd(count + leaf, 1);  // result unused: a fire-and-forget RED
+		if (st == ST_OK) atomicAdd(count + eval_cell<NT>(m, x, leaf), 1);  // result unused: a fire-and-forget RED
 		else out[i] = __longlong_as_double(0x7ff8000000000000LL);
 	}
 }
@@ -157,6 +184,15 @@ __global__ void __launch_bounds__(256) sorted_scatter_kernel(DeviceModel m, cons
 		}
 	}
 	int64_t pos[kScatterItems];
+	if (m.ecell_off) {  // sort key = evaluation cell (needs the cube coordinates before the atomic)
+#pragma unroll
+		for (int k = 0; k < kScatterItems; k++)
+			if (st[k] == ST_OK) {
+				Coord<NT> x;
+				map_to_cube<NT>(m, p[k], x);
+				leaf[k] = eval_cell<NT>(m, x, leaf[k]);
+			}
+	}
 #pragma unroll
 	for (int k = 0; k < kScatterItems; k++)
 		if (st[k] == ST_OK) pos[k] = atomicAdd(cursor + leaf[k], 1);
@@ -190,7 +226,7 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 	const int N = NT > 0 ? NT : m.N;
 	constexpr int RSmax = rec_doubles(NT > 0 ? NT : kMaxN);
 	const int RS = rec_doubles(N);
-	const int64_t total = __ldg(cursor + m.L);  // number of records of this chunk
+	const int64_t total = __ldg(cursor + sort_buckets(m));  // number of records of this chunk
 	const int64_t T = (int64_t)gridDim.x * blockDim.x;
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
@@ -235,7 +271,10 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 		} else {
 			// LCSample::getInterpolationWeight / newFromWeightedSum over the leaf's term list, as in eval_scalar_direct_kernel,
 			// with weight_ * val pre-multiplied per term (term_wv)
-			if (m.mterm_off) {  // merged: one term per distinct basis function of the leaf
+			if (m.ecell_off) {  // `leaf` is the evaluation cell: only the merged terms that reach this part of the leaf
+				for (int t = __ldg(m.eterm_off + leaf), t1 = __ldg(m.eterm_off + leaf + 1); t < t1; t++)
+					r += term_value<NT, CUBIC, EXACT>(m.eterm_cs + (int64_t)t * 2 * N, __ldg(m.eterm_wv + t), x, N);
+			} else if (m.mterm_off) {  // merged: one term per distinct basis function of the leaf
 				for (int t = __ldg(m.mterm_off + leaf), t1 = __ldg(m.mterm_off + leaf + 1); t < t1; t++)
 					r += term_value<NT, CUBIC, EXACT>(m.mterm_cs + (int64_t)t * 2 * N, __ldg(m.mterm_wv + t), x, N);
 			} else {
@@ -253,7 +292,7 @@ void run_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, 
 	{ LOCO_KERNEL("sorted_count", st);
 	sorted_count_kernel<NT><<<(unsigned)((Q + 256 * kCountItems - 1) / (256 * kCountItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
 	LOCO_KERNEL("sorted_scan", st);
-	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, m.L);
+	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, sort_buckets(m));
 }
 template <int NT>
 void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortedWork &w, cudaStream_t st)
@@ -277,7 +316,7 @@ void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out,
 
 size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk)
 {
-	const size_t ints = (size_t)m.L * 2 + 1 + 3;
+	const size_t ints = (size_t)sort_buckets(m) * 2 + 1 + 3;
 	return ((ints * sizeof(int32_t) + 127) & ~(size_t)127) + (size_t)chunk * rec_doubles(m.N) * sizeof(double) + 256;
 }
 
@@ -285,8 +324,8 @@ SortedWork carve_sorted_work(const DeviceModel &m, void *base)
 {
 	SortedWork w;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
-	w.count = p; p += m.L;
-	w.cursor = p; p += m.L + 1;
+	w.count = p; p += sort_buckets(m);
+	w.cursor = p; p += sort_buckets(m) + 1;
 	w.done = reinterpret_cast<unsigned *>(p); p += 3;
 	const size_t ints = (size_t)(p - reinterpret_cast<int32_t *>(base));
 	w.xs = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(base) + ((ints * sizeof(int32_t) + 127) & ~(size_t)127));
@@ -296,7 +335,7 @@ SortedWork carve_sorted_work(const DeviceModel &m, void *base)
 // the histogram and the arrival counter must be zero before the first chunk; every count kernel leaves them zero again
 int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t st)
 {
-	cudaMemsetAsync(w.count, 0, ((size_t)m.L * 2 + 1 + 3) * sizeof(int32_t), st);
+	cudaMemsetAsync(w.count, 0, ((size_t)sort_buckets(m) * 2 + 1 + 3) * sizeof(int32_t), st);
 	return 0;
 }
 

@@ -378,6 +378,18 @@ int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t 
 	return 1;
 }
 
+__global__ void eterm_wv_kernel(DeviceModel m, double *__restrict__ eterm_wv)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < m.n_eterms) eterm_wv[t] = m.mterm_wv[m.eterm_src[t]];
+}
+int launch_update_eterm_wv(const DeviceModel &m, double *eterm_wv, cudaStream_t st)
+{
+	if (!m.eterm_src || m.n_eterms <= 0) return 0;
+	eterm_wv_kernel<<<(unsigned)((m.n_eterms + 255) / 256), 256, 0, st>>>(m, eterm_wv);
+	return 1;
+}
+
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st)
 {
 	if (T <= 0) return 0;

@@ -334,6 +334,45 @@ def test_optional_fp32_mode(N, basis, level):
     assert (diff <= 1e-5 * np.maximum(np.abs(res[0][0]), 1.0)).all(), diff.max()
 
 
+@pytest.mark.parametrize("name", ["cub2d_prototest", "lin2d_adapt6", "lin3d_adapt5"])
+def test_evaluation_cells_drop_only_zero_terms(golden, name):
+    """Sorted path keyed by evaluation cell (Flat::ecell_*): a cell's term list may only leave out terms whose weight is
+    exactly zero everywhere in the cell, so the sums must equal the per-leaf sums bit for bit — on random points and on
+    points on / next to every dyadic face of every leaf (where the cell index may round either way)."""
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    assert m.info["n_eval_cells"] > m.L and m.info["n_eval_terms"] > 0
+    rng = np.random.default_rng(11)
+    dom = m.domain.reshape(m.N, 2)
+    lo, w = dom[:, 0], dom[:, 1] - dom[:, 0]
+    pts = [lo + w * rng.random((200_000, m.N)), z["q"]]
+    fr = np.arange(33) / 32.0
+    for l in range(m.L):
+        box = m.leaf_box(l)  # cube coordinates
+        grid = np.stack(np.meshgrid(*[box[d, 0] + (box[d, 1] - box[d, 0]) * fr for d in range(m.N)], indexing="ij"), -1).reshape(-1, m.N)
+        if len(grid) > 6000:
+            grid = grid[rng.choice(len(grid), 6000, replace=False)]
+        for jitter in (0.0, 1e-15, -1e-15, 3e-7, -3e-7):
+            cube = grid + jitter * rng.choice([-1.0, 1.0], size=grid.shape)
+            pts.append(lo + w * (cube + 1.0) * 0.5)
+    q = np.concatenate(pts)
+    m.set_option("path", 4)
+    m.set_option("ecells", 0)
+    a, la, sa = m.eval(q)
+    m.set_option("ecells", 1)
+    b, lb, sb = m.eval(q)
+    m.set_option("path", 1)
+    c, lc, sc = m.eval(q)
+    assert np.array_equal(la, lb) and np.array_equal(sa, sb) and np.array_equal(la, lc) and np.array_equal(sa, sc)
+    assert (sa == 0).sum() > 200_000
+    assert np.array_equal(a, b, equal_nan=True)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    o_out, o_leaf, o_status, scale = orc.eval(q[:50_000])
+    ok = o_status == 0
+    assert np.array_equal(lb[:50_000], o_leaf) and np.array_equal(sb[:50_000], o_status)
+    assert_values_close(b[:50_000][ok], o_out[ok], scale[ok])
+
+
 def test_bucket_path_overflow_with_skewed_queries():
     """path 5 (single-pass fixed-capacity leaf buckets): a batch concentrated in a few leaves overflows their buckets;
     the overflow list must give exactly the results of the direct path."""

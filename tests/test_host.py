@@ -194,6 +194,19 @@ def test_graph_argument_validation():
     assert "could not map the sample from id" in e.value.msg
 
 
+@pytest.mark.parametrize("name,cells", [("cub2d_prototest", True), ("lin2d_adapt6", True), ("lin3d_adapt5", True), ("cub3d_boot2", False),
+                                        ("c1_lin2d_boot2", False)])
+def test_evaluation_cells_are_built_for_adaptive_scalar_trees(golden, name, cells):
+    """Flat::ecell_*: leaves with many merged terms are cut into evaluation cells; tensor-product trees have none."""
+    pb, _ = golden(name)
+    info = capi.Model.from_proto(pb, device=capi.HOST_ONLY).info
+    if cells:
+        assert info["n_eval_cells"] > info["n_leaves"]
+        assert 0 < info["n_eval_terms"] <= 32 * info["n_terms"]
+    else:
+        assert info["n_eval_cells"] == 0 and info["n_eval_terms"] == 0
+
+
 def test_mesh_valued_proto_round_trip(golden, tmp_path):
     """Mesh values travel in ShapeInfo.tetMesh.vertices (PrecomputedParametricShape.proto:87-99; the slot the public
     reference no longer reads, LCProtoConverter.cpp:211-263): D = 3 * #vertices doubles per value.  A file written by
