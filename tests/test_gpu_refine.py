@@ -1,0 +1,52 @@
+"""GPU-assisted refinement pass: the batched decideSplit of `locointerpolate_b200.refine` drives the
+REFERENCE's own refineCell (compiled under oracle/_ref — test infrastructure playing the host that owns the grid).
+Every pass checks the device's per-leaf centre errors and split flags against the reference's decideSplit data on the
+same grid state; at the end the refined tree evaluates like the reference's own LCSampledFunction over that grid."""
+import numpy as np
+import pytest
+
+from locointerpolate_b200 import capi, refine
+from oracle import oracleapi, refapi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref (the compiled reference) is not built")
+@pytest.mark.parametrize("basis,max_level,threshold", [(capi.LINEAR, 8, 0.05), (capi.CUBIC, 7, 0.1)])
+def test_level_synchronous_refinement_with_reference_surgery(basis, max_level, threshold):
+    # bootstrap only: maxLevel 0 keeps the reference's own adaptiveSample from splitting anything (LCAdaptiveGrid.cpp:583)
+    grid = refapi.RefGrid(2, basis, False, 0, threshold, 2)
+    state = {}
+
+    def get_model():
+        fn = grid.sampled_function()
+        m = capi.Model.from_graph(oracleapi.graph_from_ref(fn.graph()), device=0)
+        err, split = m.center_error(threshold)
+        ref_err = np.array([fn.center_error(l) for l in range(fn.L)])
+        assert m.L == fn.L == grid.num_leaves()
+        assert np.allclose(err, ref_err, rtol=0, atol=1e-13)
+        assert np.array_equal(split.astype(bool), ~((ref_err - threshold) <= 0))  # LCAdaptiveGrid.cpp:601
+        state["fn"], state["m"] = fn, m
+        return m
+
+    log = refine.adaptive_sample_passes(get_model, grid.refine, threshold, max_level)
+    assert len(log) > 2 and log[-1]["flagged"] == 0 and log[-1]["leaves"] > log[0]["leaves"] == 16
+    assert sum(p["flagged"] for p in log) == log[-1]["leaves"] - 16  # every split adds one leaf
+    # no leaf below the level limit is left with an error above the threshold
+    m, fn = state["m"], state["fn"]
+    err, split = m.center_error(threshold)
+    _, level = refine.leaf_geometry(m)
+    assert not (split.astype(bool) & (level < max_level)).any()
+    # the refined tree evaluates like the reference's LCSampledFunction over the same grid
+    q = np.random.default_rng(3).random((4000, 2))
+    out, leaf, status = m.eval(q)
+    r_out, r_leaf, r_status = fn.eval(q)
+    assert np.array_equal(leaf, r_leaf) and np.array_equal(status, r_status)
+    ok = status == 0
+    assert np.abs(out[ok] - r_out[ok]).max() <= 1e-12 * max(1.0, np.abs(r_out[ok]).max())
+    # and it approximates the sampled function about as well as the reference's sequential schedule does
+    seq = refapi.RefGrid(2, basis, False, max_level, threshold, 2)
+    truth = grid.true_values(q)
+    s_out, _, s_status = seq.sampled_function().eval(q)
+    e_pass, e_seq = np.abs(out[ok] - truth[ok]).max(), np.abs(s_out[s_status == 0] - truth[s_status == 0]).max()
+    assert e_pass <= 2.0 * max(e_seq, threshold), (e_pass, e_seq, log[-1]["leaves"], seq.num_leaves())
