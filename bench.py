@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the batched LCSampledFunction evaluation hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c4b|c5|a1] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic queries (per GPU; weak scaling: the batch
 per GPU is fixed as N grows, the model is replicated, queries are independent).  Rank 0 prints ONE JSON line.
@@ -45,6 +45,10 @@ WORKLOADS = {
     "c4b": dict(N=6, basis=1, level=2, D=150_000, corners=False, Q=262_144, ring=16_384,
                 desc="6-D cubic mesh-valued (50k vertices, D=150,000), bootstrap 2 (4,096 leaves at depth 12, 15,625 value rows = 18.75 GB, K=4,096); "
                      "262,144 queries per step sorted once and streamed through a 16,384-query ring (19.7 GB) with a per-query checksum"),
+    # not a BASELINE config: the reference's own adaptively refined tree (its builder's output, committed as a fixture)
+    "a1": dict(N=2, basis=1, level=-1, D=1, corners=True, Q=100_000_000, proto="tests/golden/cub2d_testdebug.pb.gz",
+               desc="2-D cubic scalar on the reference's TestDebug tree (TestDebug.cpp:153-157: maxDepth 10, threshold 0.1, bootstrap 2 -> "
+                    "724 leaves at levels 4-10, 1,063 samples, 54,419 basis functions), generic term-list kernels, 100M queries"),
     "c5": dict(N=8, basis=0, level=1, D=1, corners=True, Q=64_000_000,
                desc="8-D linear scalar error check, bootstrap 1 (256 leaves, K=256); 1B candidate points per pass in 64M-point batches"),
 }
@@ -109,6 +113,15 @@ def measured_peak():
 
 def build_model(capi, w, device):
     f, amp, phase = test_function(w["N"])
+    if w.get("proto"):  # a committed model file (gzip-compressed proto written by the reference's builder)
+        import gzip
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".pb", delete=False) as t:
+            t.write(gzip.open(os.path.join(ROOT, w["proto"]), "rb").read())
+        try:
+            return capi.Model.from_proto(t.name, device=device), amp, phase
+        finally:
+            os.unlink(t.name)
     if w["D"] == 1:
         m = capi.Model.bootstrap(w["N"], w["basis"], w["level"], 1, w["corners"], fn=f, device=device)
     else:
@@ -205,7 +218,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000}[args.workload]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[args.workload]
         base, dt = cpu_reference_arm(w, args.cpu_sample or cpu_default, max(args.steps, 1), args.warmup, args.workload)
         print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": "queries/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -502,7 +515,7 @@ def measure(name, w, args, rank, world, local, config, full):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000}[name]
+        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[name]
         try:
             cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, name)
         except SystemExit as e:

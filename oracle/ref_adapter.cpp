@@ -602,15 +602,23 @@ int ref_fn_num_neighbors(void *fp, int leafIdx)
 	return (int)r->leaves[leafIdx]->getNeighbors().size();
 }
 
-// The refinement-loop error check for one leaf, CENTER_BASED (LCAdaptiveGrid.cpp:594-602 via
-// LCAdaptiveGridCell::getApproximationError, LCAdaptiveGridCell.cpp:1088-1100): |interp(centre) - f(centre)|.
+// The refinement-loop error check for one leaf, CENTER_BASED, with the calls decideSplit makes (LCAdaptiveGrid.cpp:586-596):
+// |interp(centre) - f(centre)|.  (LCAdaptiveGridCell::getApproximationError does the same but takes the basis type from
+// the cell's own samples, LCAdaptiveGridCell.cpp:1105-1118 — uninitialised, and a crash, for a leaf of a deeply refined tree
+// whose own samples have lost all their basis functions to the locality repair; decideSplit uses the grid's basisType_.)
 double ref_fn_center_error(void *fp, int leafIdx)
 {
 	CoutMute mute;
 	RefFn *r = (RefFn *)fp;
+	LCAdaptiveGridCell *cell = r->leaves[leafIdx];
+	std::vector<double> center;
+	cell->getCenter(&center);
+	LCFunctionValue *approx = nullptr;
+	if (!cell->evalShapeInfo(center, (LCBasisFunction::LCBasisFunctionType)r->basis, &approx).isOK()) return NAN;
 	Eigen::VectorXd e;
-	if (!r->leaves[leafIdx]->getApproximationError(&e).isOK()) return NAN;
-	return e(0);
+	const bool ok = approx->computeErrorVector(cell->getCenterShapeInfo(), &e).isOK();
+	delete approx;
+	return ok ? e(0) : NAN;
 }
 
 } // extern "C"

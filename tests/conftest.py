@@ -10,7 +10,25 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pb")))
+# larger trees are committed gzip-compressed (<name>.pb.gz) and unpacked on first use into tests/golden/_unpacked/
+GOLDEN_CASES = sorted([os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, "*.pb"))] +
+                      [os.path.basename(p)[:-6] for p in glob.glob(os.path.join(GOLDEN, "*.pb.gz"))])
+
+
+def golden_proto_path(name):
+    """path of the proto file of a golden case (unpacking <name>.pb.gz if that is how it is stored)"""
+    plain = os.path.join(GOLDEN, name + ".pb")
+    if os.path.exists(plain):
+        return plain
+    import gzip
+    out = os.path.join(GOLDEN, "_unpacked", name + ".pb")
+    if not os.path.exists(out):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        tmp = out + f".{os.getpid()}.tmp"
+        with gzip.open(plain + ".gz", "rb") as f, open(tmp, "wb") as o:
+            o.write(f.read())
+        os.replace(tmp, out)
+    return out
 
 # fp64 value parity bar from BASELINE.json north_star: 1e-12 relative.  The reference is not
 # bit-reproducible against itself (summation order = hash iteration order, SURVEY.md 8a / H2), and a
@@ -36,7 +54,7 @@ def assert_values_close(got, ref, scale, rtol=VALUE_RTOL):
 @pytest.fixture(scope="session")
 def golden():
     def load(name):
-        return os.path.join(GOLDEN, name + ".pb"), np.load(os.path.join(GOLDEN, name + ".npz"))
+        return golden_proto_path(name), np.load(os.path.join(GOLDEN, name + ".npz"))
     return load
 
 

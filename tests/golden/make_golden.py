@@ -38,7 +38,11 @@ CASES = {
     "cub3d_boot2": (3, 1, False, 0, 0.1, 2, True, None),
     "cub3d_boot1_nocorner": (3, 1, False, 0, 0.1, 1, False, None),
     "lin4d_boot1": (4, 0, False, 0, 0.1, 1, True, None),
+    # the TestDebug tree (TestDebug.cpp:153-157): 2-D cubic, maxDepth 10, threshold 0.1, bootstrap 2 -> 724 leaves,
+    # 54,419 basis functions; ~30 s to build, 2.8 MB of proto -> stored as .pb.gz
+    "cub2d_testdebug": (2, 1, False, 10, 0.1, 2, True, None),
 }
+GZIPPED = {"cub2d_testdebug"}
 
 
 def queries(N, n, seed):
@@ -56,7 +60,10 @@ def queries(N, n, seed):
 
 
 def main():
+    only = set(sys.argv[1:])  # python make_golden.py [case ...]: regenerate only the named cases
     for name, (N, basis, lin, depth, thr, boot, corners, refine) in CASES.items():
+        if only and name not in only:
+            continue
         g = refapi.RefGrid(N, basis, lin, depth, thr, boot, 0, corners)
         if refine:
             g.refine_random(*refine)
@@ -72,8 +79,15 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), q=q, out=out, leaf=leaf, status=status, sup_off=sup_off,
                             sup_ids=np.concatenate(sup).astype(np.int32), n_neighbors=nn, center_err=cerr,
                             true_values=g.true_values(q))
+        if name in GZIPPED:
+            import gzip
+            pb = os.path.join(HERE, name + ".pb")
+            with open(pb, "rb") as f, gzip.GzipFile(pb + ".gz", "wb", compresslevel=9, mtime=0) as o:
+                o.write(f.read())
         print(f"{name}: N={N} basis={basis} leaves={fn.L} samples={fn.S} basis_fns={fn.B} border={fn.Bc} "
               f"bad={int((status != 0).sum())} pb={os.path.getsize(os.path.join(HERE, name + '.pb'))}B")
+        if name in GZIPPED:
+            os.unlink(os.path.join(HERE, name + ".pb"))
 
 
 if __name__ == "__main__":

@@ -6,7 +6,6 @@ For every committed <name>.pb the graph is re-materialised as reference objects 
 path without protobuf) and the reference's LCSampledFunction::evalDeriv (LCSampledFunction.cpp:61-67) is run on the
 fixture's queries along every cube direction.  Stored: deriv [N, Q] (NaN where the reference returned an LCError).
 """
-import glob
 import os
 import sys
 
@@ -21,8 +20,12 @@ import protoschema  # noqa: E402
 
 
 def main():
-    for pb in sorted(glob.glob(os.path.join(HERE, "*.pb"))):
-        name = os.path.basename(pb)[:-3]
+    from conftest import GOLDEN_CASES, golden_proto_path
+    only = set(sys.argv[1:])  # python make_golden_deriv.py [case ...]
+    for name in GOLDEN_CASES:
+        if only and name not in only:
+            continue
+        pb = golden_proto_path(name)
         z = np.load(os.path.join(HERE, name + ".npz"))
         fn = refapi.RefFn.from_graph(protoschema.read_binary(pb))
         deriv = np.stack([fn.eval_deriv(z["q"], d) for d in range(fn.N)])

@@ -3,11 +3,13 @@ reference's own code, the CPU restatement in oracle/, and size-independent prope
 
 Bars (BASELINE.json north_star): leaf indices, status bytes and support sets bit-exact; fp64 values within
 1e-12 relative (see conftest.VALUE_RTOL for what "relative" is taken against)."""
+import os
+
 import numpy as np
 import pytest
 
 import protoschema
-from conftest import GOLDEN_CASES, assert_values_close
+from conftest import GOLDEN, GOLDEN_CASES, assert_values_close
 from locointerpolate_b200 import capi
 from oracle import oracleapi
 
@@ -180,7 +182,7 @@ def test_mesh_ring_checksum():
 def test_derivative_golden_vectors(golden, name):
     """LCSampledFunction::evalDeriv batch vs the reference's own output and vs the restatement."""
     pb, z = golden(name)
-    ref = np.load(pb[:-3] + ".deriv.npz")["deriv"]
+    ref = np.load(os.path.join(GOLDEN, name + ".deriv.npz"))["deriv"]
     m = capi.Model.from_proto(pb, device=0)
     orc = oracleapi.Oracle(protoschema.read_binary(pb))
     for d in range(m.N):
@@ -334,7 +336,7 @@ def test_optional_fp32_mode(N, basis, level):
     assert (diff <= 1e-5 * np.maximum(np.abs(res[0][0]), 1.0)).all(), diff.max()
 
 
-@pytest.mark.parametrize("name", ["cub2d_prototest", "lin2d_adapt6", "lin3d_adapt5"])
+@pytest.mark.parametrize("name", ["cub2d_prototest", "lin2d_adapt6", "lin3d_adapt5", "cub2d_testdebug"])
 def test_evaluation_cells_drop_only_zero_terms(golden, name):
     """Sorted path keyed by evaluation cell (Flat::ecell_*): a cell's term list may only leave out terms whose weight is
     exactly zero everywhere in the cell, so the sums must equal the per-leaf sums bit for bit — on random points and on

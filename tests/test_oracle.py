@@ -1,10 +1,12 @@
 """The oracle (oracle/loco_oracle.cpp) pinned against the reference: committed golden vectors produced by
 the reference's own code, and -- where oracle/_ref/liblocoref.so is present -- the compiled reference live."""
+import os
+
 import numpy as np
 import pytest
 
 import protoschema
-from conftest import GOLDEN_CASES, assert_values_close
+from conftest import GOLDEN, GOLDEN_CASES, assert_values_close
 from oracle import oracleapi, refapi
 
 
@@ -117,7 +119,7 @@ def test_oracle_derivative_matches_golden(golden, name):
     including the reference's signed-distance test (LCBasisFunction.cpp:295-332)."""
     import os
     pb, z = golden(name)
-    ref = np.load(pb[:-3] + ".deriv.npz")["deriv"]
+    ref = np.load(os.path.join(GOLDEN, name + ".deriv.npz"))["deriv"]
     orc = oracleapi.Oracle(protoschema.read_binary(pb))
     for d in range(orc.N):
         out, leaf, status, scale = orc.eval_deriv(z["q"], d)
