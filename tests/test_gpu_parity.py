@@ -243,6 +243,50 @@ def test_locate_grid_equals_descent_bootstrap(N, basis, level):
     assert leaf1.max() == m.L - 1
 
 
+@pytest.mark.parametrize("N,level", [(9, 1), (10, 0), (12, 0)])
+def test_more_than_eight_parameters_every_path(N, level, tmp_path):
+    """N > 8 runs the runtime-N instantiation of every kernel (coordinates in local memory instead of unrolled
+    registers): scalar values on every path, derivatives, the centre error check and a mesh-valued function."""
+    def f(p):
+        return 1 + np.sin(3 * p + np.arange(len(p))).sum()
+    m = capi.Model.bootstrap(N, capi.LINEAR, level, 1, True, fn=f, device=0)
+    path = str(tmp_path / "m.pb")
+    m.save_proto(path)
+    orc = oracleapi.Oracle(protoschema.read_binary(path))
+    rng = np.random.default_rng(21)
+    q = rng.random((8_000, N)) * 1.000002 - 0.000001
+    q[:512] = np.round(q[:512] * 2) / 2  # on split planes and sample positions
+    q[np.arange(600, 640), rng.integers(0, N, 40)] += 1.5 * rng.choice([-1.0, 1.0], 40)  # outside the domain in one coordinate
+    o_out, o_leaf, o_status, scale = orc.eval(q)
+    ok = o_status == 0
+    assert ok.sum() > 7_000 and (~ok).sum() >= 30
+    for p_ in (0, 1, 2, 3, 4, 5):
+        m.set_option("path", p_)
+        out, leaf, status = m.eval(q)
+        assert np.array_equal(leaf, o_leaf) and np.array_equal(status, o_status), p_
+        assert_values_close(out[ok], o_out[ok], scale[ok])
+        assert np.isnan(out[~ok]).all()
+    m.set_option("path", 0)
+    for d in (0, N - 1):
+        out, leaf, status = m.eval_deriv(q[:4000], d)
+        d_out, d_leaf, d_status, d_scale = orc.eval_deriv(q[:4000], d)
+        assert np.array_equal(leaf, d_leaf) and np.array_equal(status, d_status)
+        assert_values_close(out[d_status == 0], d_out[d_status == 0], d_scale[d_status == 0])
+    err, split = m.center_error(0.05)
+    o_err, o_split = orc.center_error(0.05)
+    assert np.allclose(err, o_err, rtol=0, atol=1e-12) and np.array_equal(split, o_split)
+    # mesh-valued on the same tree: component j equals the scalar function scaled by (j + 1)
+    D = 5
+    mesh = capi.Model.bootstrap(N, capi.LINEAR, level, D, True, fn=lambda p: f(p) * (1 + np.arange(D)), device=0)
+    for simt, p_ in ((0, 0), (1, 0), (0, 1)):
+        mesh.set_option("mesh_simt", simt)
+        mesh.set_option("path", p_)
+        mo, ml, ms = mesh.eval(q[:3000])
+        assert np.array_equal(ml, o_leaf[:3000]) and np.array_equal(ms, o_status[:3000])
+        for j in range(D):
+            assert_values_close(mo[ok[:3000], j], o_out[:3000][ok[:3000]] * (j + 1), scale[:3000][ok[:3000]] * (j + 1))
+
+
 @pytest.mark.parametrize("N,level", [(2, 1), (3, 2), (4, 1)])
 def test_mesh_valued_shared_border_rows(N, level):
     """Cubic grids built with evalCorners=false: border samples share the value object of their clamped in-domain
