@@ -42,12 +42,13 @@ __device__ __forceinline__ void map_to_cube(const DeviceModel &m, const double *
 	}
 }
 
-// LCAdaptiveGridCell::getCointainingLeaf (LCAdaptiveGridCell.cpp:260-272): strict '<' sends ties to child2.
-// One 16-byte read-only load per INNER level; the child codes name the leaf directly (see TreeCell).
+// Point location in two halves.
+// first half: the locate-grid lookup.  Returns the code of the deepest tree cell known to contain x (leaf-flagged if
+// it is a leaf), 0 = start at the root.  Split from the descent so that callers with several queries per thread can
+// issue all their lookups before consuming any of them.
 template <int NT>
-__device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT> &x)
+__device__ __forceinline__ uint32_t lut_lookup(const DeviceModel &m, const Coord<NT> &x)
 {
-	if (m.n_inner == 0) return 0;  // the root is a leaf
 	uint32_t c = 0;
 	if (m.lut) {
 		// locate grid: the grid cell is found with EXACT comparisons against the stored boundaries (the
@@ -74,8 +75,17 @@ __device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT>
 			shift += bits;
 		}
 		if (ok) c = __ldg(m.lut + idx);
-		if (c & kLeafFlag) return (int32_t)(c & (kLeafFlag - 1));
 	}
+	return c;
+}
+
+// second half: LCAdaptiveGridCell::getCointainingLeaf (LCAdaptiveGridCell.cpp:260-272) from tree cell `c` down: strict '<'
+// sends ties to child2.  One 16-byte read-only load per INNER level; the child codes name the leaf directly (see TreeCell).
+template <int NT>
+__device__ __forceinline__ int32_t descend_from(const DeviceModel &m, const Coord<NT> &x, uint32_t c)
+{
+	if (m.n_inner == 0) return 0;  // the root is a leaf
+	if (c & kLeafFlag) return (int32_t)(c & (kLeafFlag - 1));
 	for (;;) {
 		const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(m.cells + c));
 		const double split = __hiloint2double((int)raw.y, (int)raw.x);
@@ -83,6 +93,13 @@ __device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT>
 		if (next & kLeafFlag) return (int32_t)(next & (kLeafFlag - 1));
 		c = next;
 	}
+}
+
+template <int NT>
+__device__ __forceinline__ int32_t descend(const DeviceModel &m, const Coord<NT> &x)
+{
+	if (m.n_inner == 0) return 0;  // the root is a leaf
+	return descend_from<NT>(m, x, lut_lookup<NT>(m, x));
 }
 
 // LCAdaptiveGridCell::evalPametersAreInCell (:438-454) against lo-EPSILON / hi+EPSILON precomputed on the

@@ -43,33 +43,55 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 {
 	constexpr int RS = brec_doubles(NT);
 	const int64_t i0 = (int64_t)blockIdx.x * (256 * kItems) + threadIdx.x;
-	double p[kItems][NT];
+	// Phases instead of one query after the other: a thread's kItems dependent chains
+	// (query -> locate-grid entry -> bucket counter -> record) advance together, one memory round trip per phase.
+	Coord<NT> x[kItems];
+	uint32_t code[kItems];
+	bool live[kItems];
+	{
+		double p[kItems][NT];
 #pragma unroll
-	for (int k = 0; k < kItems; k++) {
-		const int64_t i = i0 + k * 256;
-		if (i < Q) {
+		for (int k = 0; k < kItems; k++) {
+			const int64_t i = i0 + k * 256;
+			live[k] = i < Q;
+			if (live[k]) {
 #pragma unroll
-			for (int d = 0; d < NT; d++) p[k][d] = __ldcs(q + i * NT + d);
+				for (int d = 0; d < NT; d++) p[k][d] = __ldcs(q + i * NT + d);
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < kItems; k++) {
+			code[k] = 0;
+			if (live[k]) {
+				map_to_cube<NT>(m, p[k], x[k]);
+				code[k] = lut_lookup<NT>(m, x[k]);
+			}
 		}
 	}
+	int32_t leaf[kItems], slot[kItems];
 #pragma unroll
 	for (int k = 0; k < kItems; k++) {
+		if (!live[k]) continue;
 		const int64_t i = i0 + k * 256;
-		if (i >= Q) continue;
-		Coord<NT> x;
-		map_to_cube<NT>(m, p[k], x);
-		const int32_t leaf = descend<NT>(m, x);
-		const uint8_t st = located_status<NT>(m, x, leaf);
-		__stcs(leaf_out + i, leaf);
+		leaf[k] = descend_from<NT>(m, x[k], code[k]);
+		const uint8_t st = located_status<NT>(m, x[k], leaf[k]);
+		__stcs(leaf_out + i, leaf[k]);
 		status_out[i] = st;
-		if (st != ST_OK) { out[i] = __longlong_as_double(0x7ff8000000000000LL); continue; }
-		const int32_t slot = atomicAdd(count + leaf, 1);
-		if (slot < cap) {
+		if (st != ST_OK) { out[i] = __longlong_as_double(0x7ff8000000000000LL); live[k] = false; }
+	}
+#pragma unroll
+	for (int k = 0; k < kItems; k++)
+		if (live[k]) slot[k] = atomicAdd(count + leaf[k], 1);
+#pragma unroll
+	for (int k = 0; k < kItems; k++) {
+		if (!live[k]) continue;
+		const int64_t i = i0 + k * 256;
+		if (slot[k] < cap) {
 			double v[RS];
 #pragma unroll
-			for (int d = 0; d < RS; d++) v[d] = d < NT ? x.get(d) : 0.0;
+			for (int d = 0; d < RS; d++) v[d] = d < NT ? x[k].get(d) : 0.0;
 			v[RS - 1] = __longlong_as_double((long long)(int32_t)i);
-			double *row = rec + ((int64_t)leaf * cap + slot) * RS;
+			double *row = rec + ((int64_t)leaf[k] * cap + slot[k]) * RS;
 #pragma unroll
 			for (int d = 0; d < RS; d += 4) st_sector_cg(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
 		} else {
@@ -78,57 +100,86 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 	}
 }
 
-// one warp per leaf; 8 warps per CTA, each with its own shared-memory copy of its current leaf block
-template <int NT, bool CUBIC, bool EXACT, bool FP32>
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// one warp per leaf; 8 warps per CTA, each with its own shared-memory copies of its current and (DBL) its next leaf block.
+// The three dependent round trips of a leaf (counter -> block + first records -> arithmetic) are software-pipelined ACROSS
+// leaves: while leaf l is evaluated, the counter of leaf l' = l + #warps has been read, its block is on its way into the
+// other shared-memory slot (cp.async) and its first 32 records are loaded during the last record group of l.
+template <int NT, bool CUBIC, bool EXACT, bool FP32, bool DBL>
 __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out,
                                                               const double *__restrict__ q, const int32_t *__restrict__ leaf_in, const int32_t *__restrict__ ovf,
                                                               const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0) *n_ovf_next = 0;  // the counter of the NEXT chunk on this workspace (nobody reads it now)
 	constexpr int RS = brec_doubles(NT);
-	extern __shared__ __align__(16) double s_blk[];  // [8][tl_stride]  (+ [8][K/2] doubles holding the fp32 values in fp32 mode)
+	extern __shared__ __align__(16) double s_blk[];  // [8][DBL ? 2 : 1][tl_stride]  (+ K/2 doubles per slot holding the fp32 values in fp32 mode)
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n_warps = gridDim.x * 8;
-	const int blk_doubles = FP32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride;
-	double *blk = s_blk + (size_t)warp * ((blk_doubles + 1) & ~1);
-	for (int32_t leaf = blockIdx.x * 8 + warp; leaf < m.L; leaf += n_warps) {
-		const int32_t n = min(count[leaf], cap);
-		if (n == 0) continue;
-		__syncwarp();  // every lane is done with the previous leaf's block
-		if (lane == 0) count[leaf] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
-		// ---- the leaf's block into this warp's slot: 128-bit loads, all in flight together
-		{
-			const double2 *src = reinterpret_cast<const double2 *>(m.tl_block + (int64_t)leaf * m.tl_stride);
-			const int n2 = (FP32 ? m.tl_voff : m.tl_stride) / 2;
-			for (int e = lane; e < n2; e += 32) reinterpret_cast<double2 *>(blk)[e] = __ldg(src + e);
-			if (FP32) {
-				const float4 *vs = reinterpret_cast<const float4 *>(m.tl_vals_f32 + (int64_t)leaf * m.tensor_K);
-				float4 *dst = reinterpret_cast<float4 *>(blk + m.tl_voff);
-				for (int e = lane; e < m.tensor_K / 4; e += 32) dst[e] = __ldg(vs + e);
-			}
+	const int slot_doubles = ((FP32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
+	double *slot0 = s_blk + (size_t)warp * (DBL ? 2 : 1) * slot_doubles;
+	auto issue_block = [&](int32_t lf, double *dst) {
+		const char *src = reinterpret_cast<const char *>(m.tl_block + (int64_t)lf * m.tl_stride);
+		const int n16 = (FP32 ? m.tl_voff : m.tl_stride) / 2;
+		for (int e = lane; e < n16; e += 32) cp_async16(dst + 2 * e, src + 16 * e);
+		if (FP32) {
+			const char *vs = reinterpret_cast<const char *>(m.tl_vals_f32 + (int64_t)lf * m.tensor_K);
+			for (int e = lane; e < m.tensor_K / 4; e += 32) cp_async16(dst + m.tl_voff + 2 * e, vs + 16 * e);
 		}
-		__syncwarp();
-		const double *bucket = rec + (int64_t)leaf * cap * RS;
-		// ---- 32 records at a time, the next group's records prefetched while this group is evaluated
-		double nv[RS];
-		if (lane < n) {
+		cp_async_commit();
+	};
+	double nv[RS];
+	auto load_rec = [&](const double *row) {
 #pragma unroll
-			for (int d = 0; d < RS; d += 4) ld_sector_cg(bucket + (int64_t)lane * RS + d, nv[d], nv[d + 1], nv[d + 2], nv[d + 3]);
-		}
-		for (int s = lane; s < n; s += 32) {
+		for (int d = 0; d < RS; d += 4) ld_sector_cg(row + d, nv[d], nv[d + 1], nv[d + 2], nv[d + 3]);
+	};
+	int32_t leaf = blockIdx.x * 8 + warp, n = 0;
+	int buf = 0;
+	if (leaf < m.L) {
+		n = min(count[leaf], cap);
+		issue_block(leaf, slot0);
+		load_rec(rec + ((int64_t)leaf * cap + lane) * RS);  // a bucket has >= 32 slots; lanes beyond n read unused memory
+	}
+	while (leaf < m.L) {
+		const int32_t next = leaf + n_warps;
+		const bool more = next < m.L;
+		int32_t n_next = 0;
+		if (more) n_next = count[next];
+		if (DBL && more) { issue_block(next, slot0 + (buf ^ 1) * slot_doubles); cp_async_wait<1>(); }
+		else cp_async_wait<0>();
+		__syncwarp();
+		if (lane == 0 && n > 0) count[leaf] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
+		const double *blk = slot0 + (DBL ? buf : 0) * slot_doubles;
+		const double *bucket = rec + (int64_t)leaf * cap * RS;
+		const double *nbucket = rec + ((int64_t)next * cap + lane) * RS;
+		if (n == 0 && more) load_rec(nbucket);
+		// ---- 32 records at a time, the next group's (or the next leaf's first) records prefetched while this group is evaluated
+		for (int g0 = 0; g0 < n; g0 += 32) {
+			const int s = g0 + lane;
 			Coord<NT> x;
 #pragma unroll
 			for (int d = 0; d < NT; d++) x.set(d, nv[d]);
 			const int32_t qi = (int32_t)__double_as_longlong(nv[RS - 1]);
-			if (s + 32 < n) {
-#pragma unroll
-				for (int d = 0; d < RS; d += 4) ld_sector_cg(bucket + (int64_t)(s + 32) * RS + d, nv[d], nv[d + 1], nv[d + 2], nv[d + 3]);
+			if (g0 + 32 < n) { if (s + 32 < n) load_rec(bucket + (int64_t)(s + 32) * RS); }
+			else if (more) load_rec(nbucket);
+			if (s < n) {
+				double r;
+				if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
+				else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
+				out[qi] = r;
 			}
-			double r;
-			if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
-			else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
-			out[qi] = r;
 		}
+		__syncwarp();  // every lane is done with this leaf's block before its slot is written again
+		if (!DBL && more) issue_block(next, slot0);
+		leaf = next;
+		n = min(n_next, cap);
+		buf ^= 1;
 	}
 	// ---- the overflow list (queries whose bucket was full; normally empty): one thread each, straight from the global leaf blocks
 	const int32_t n_over = *n_ovf;
@@ -174,18 +225,16 @@ void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, in
 	{
 		LOCO_KERNEL("bucket_eval", st);
 		const bool f32 = fp32 && m.tl_vals_f32 && (m.tensor_K % 4) == 0;
-		const int blk_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
-		const size_t smem = (size_t)8 * blk_doubles * sizeof(double);
+		const int slot_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
+		const bool dbl = (size_t)16 * slot_doubles * sizeof(double) <= 72 * 1024;  // two slots per warp while 3 CTAs per SM still fit
+		const size_t smem = (size_t)8 * (dbl ? 2 : 1) * slot_doubles * sizeof(double);
 		const int grid = std::min(sm_count * 3, (m.L + 7) / 8);
-		if (f32) {
-			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, true>;
+		auto launch = [&](auto kern) {
 			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next);
-		} else {
-			auto kern = bucket_eval_kernel<NT, CUBIC, EXACT, false>;
-			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next);
-		}
+		};
+		if (f32) { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, true>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, false>); }
+		else { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, true>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, false>); }
 	}
 }
 
