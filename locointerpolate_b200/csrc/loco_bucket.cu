@@ -112,10 +112,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // The three dependent round trips of a leaf (counter -> block + first records -> arithmetic) are software-pipelined ACROSS
 // leaves: while leaf l is evaluated, the counter of leaf l' = l + #warps has been read, its block is on its way into the
 // other shared-memory slot (cp.async) and its first 32 records are loaded during the last record group of l.
-template <int NT, bool CUBIC, bool EXACT, bool FP32, bool DBL>
+// DERIV (cubic, fp64): the derivative along cube direction `dir` instead of the value (LCSampledFunction::evalDeriv).
+template <int NT, bool CUBIC, bool EXACT, bool FP32, bool DBL, bool DERIV>
 __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out,
                                                               const double *__restrict__ q, const int32_t *__restrict__ leaf_in, const int32_t *__restrict__ ovf,
-                                                              const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next)
+                                                              const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next, int dir)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0) *n_ovf_next = 0;  // the counter of the NEXT chunk on this workspace (nobody reads it now)
 	constexpr int RS = brec_doubles(NT);
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 			else if (more) load_rec(nbucket);
 			if (s < n) {
 				double r;
-				if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
+				if constexpr (DERIV) r = tensor_eval_scalar_deriv<NT, EXACT>(m, blk, x, dir);
+				else if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
 				else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
 				out[qi] = r;
 			}
@@ -190,31 +192,15 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 #pragma unroll
 		for (int d = 0; d < NT; d++) p[d] = q[(int64_t)i * NT + d];
 		map_to_cube<NT>(m, p, x);
-		out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf_in[i] * m.tl_stride, x);
+		const double *gblk = m.tl_block + (int64_t)leaf_in[i] * m.tl_stride;
+		if constexpr (DERIV) out[i] = tensor_eval_scalar_deriv<NT, EXACT>(m, gblk, x, dir);
+		else out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, gblk, x);
 	}
 }
-
-// (kept for reference) the overflow list as a kernel of its own
-template <int NT, bool CUBIC, bool EXACT>
-__global__ void __launch_bounds__(256) overflow_eval_kernel(DeviceModel m, const double *__restrict__ q, const int32_t *__restrict__ leaf_in,
-                                                             const int32_t *__restrict__ ovf, int32_t *n_ovf, double *__restrict__ out)
-{
-	const int32_t n = *n_ovf;
-	for (int32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-		const int32_t i = ovf[e];
-		Coord<NT> x;
-		double p[NT];
-#pragma unroll
-		for (int d = 0; d < NT; d++) p[d] = q[(int64_t)i * NT + d];
-		map_to_cube<NT>(m, p, x);
-		out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf_in[i] * m.tl_stride, x);
-	}
-}
-__global__ void overflow_reset_kernel(int32_t *n_ovf) { *n_ovf = 0; }
 
 template <int NT, bool CUBIC, bool EXACT>
 void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w, int sm_count, bool fp32,
-               int parity, cudaStream_t st)
+               int parity, int deriv_dir, cudaStream_t st)
 {
 	// overflow counters alternate between the chunks of a workspace: the evaluation of chunk j clears the counter of chunk j+1
 	int32_t *n_ovf = w.n_ovf + (parity & 1), *n_ovf_next = w.n_ovf + ((parity + 1) & 1);
@@ -224,17 +210,23 @@ void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, in
 	}
 	{
 		LOCO_KERNEL("bucket_eval", st);
-		const bool f32 = fp32 && m.tl_vals_f32 && (m.tensor_K % 4) == 0;
+		const bool f32 = fp32 && m.tl_vals_f32 && (m.tensor_K % 4) == 0 && deriv_dir < 0;
 		const int slot_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
 		const bool dbl = (size_t)16 * slot_doubles * sizeof(double) <= 72 * 1024;  // two slots per warp while 3 CTAs per SM still fit
 		const size_t smem = (size_t)8 * (dbl ? 2 : 1) * slot_doubles * sizeof(double);
 		const int grid = std::min(sm_count * 3, (m.L + 7) / 8);
 		auto launch = [&](auto kern) {
 			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next, deriv_dir);
 		};
-		if (f32) { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, true>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, false>); }
-		else { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, true>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, false>); }
+		if constexpr (CUBIC) {
+			if (deriv_dir >= 0) {
+				if (dbl) launch(bucket_eval_kernel<NT, true, EXACT, false, true, true>); else launch(bucket_eval_kernel<NT, true, EXACT, false, false, true>);
+				return;
+			}
+		}
+		if (f32) { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, true, false>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, false, false>); }
+		else { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, true, false>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, false, false>); }
 	}
 }
 
@@ -273,16 +265,17 @@ int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t 
 }
 
 int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w,
-                                    int sm_count, bool fp32, int parity, cudaStream_t st)
+                                    int sm_count, bool fp32, int parity, cudaStream_t st, int deriv_dir)
 {
 	if (Q <= 0) return 0;
+	if (deriv_dir >= 0 && m.basis != CUBIC_BSPLINE) return 0;  // the derivative variant exists for the cubic basis only (callers check)
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_BCASE(NT)                                                                                                                   \
 	case NT:                                                                                                                             \
-		if (cubic) { if (exact) run_chunk<NT, true, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st);                            \
-		             else run_chunk<NT, true, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st); }                               \
-		else { if (exact) run_chunk<NT, false, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st);                                 \
-		       else run_chunk<NT, false, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, st); }                                    \
+		if (cubic) { if (exact) run_chunk<NT, true, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, deriv_dir, st);                            \
+		             else run_chunk<NT, true, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, deriv_dir, st); }                               \
+		else { if (exact) run_chunk<NT, false, true>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, deriv_dir, st);                                 \
+		       else run_chunk<NT, false, false>(m, q, Q, out, leaf, status, w, sm_count, fp32, parity, deriv_dir, st); }                                    \
 		break;
 	switch (m.N) { LOCO_BCASE(1) LOCO_BCASE(2) LOCO_BCASE(3) LOCO_BCASE(4) LOCO_BCASE(5) LOCO_BCASE(6) LOCO_BCASE(7) LOCO_BCASE(8) default: return 0; }
 #undef LOCO_BCASE

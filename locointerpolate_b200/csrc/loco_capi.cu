@@ -338,8 +338,9 @@ int finish_model(loco_model *m, int device, loco_model_t **out)
 }
 
 // scalar or mesh evaluation of Q queries resident on the device, using workspace slot `w`
+// deriv_dir >= 0 (scalar functions only): LCSampledFunction::evalDeriv along that cube direction instead of the value
 int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, const double *q, int64_t Q, double *out, int64_t out_stride,
-                int32_t *leaf, uint8_t *status)
+                int32_t *leaf, uint8_t *status, int deriv_dir = -1)
 {
 	const DeviceModel &dm = m->dm;
 	if (Q <= 0) return LOCO_OK;
@@ -350,7 +351,14 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool big = Q >= (int64_t)dm.L * 24 && Q >= (1 << 16) && leaf_bytes > 96 * 1024;
 		const bool sorted = !in_cube && (m->opt_path == 4 || (m->opt_path == 0 && big));
 		const bool tiles = !in_cube && m->opt_path == 2;
-		const bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256));
+		const bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256)) &&
+		                    (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE);
+		if (deriv_dir >= 0 && !bucket) {
+			// derivatives outside the bucket path (linear basis, generic leaves, small batches): one thread per query
+			m->launches += launch_eval_deriv_direct(dm, q, Q, deriv_dir, out, leaf, status, st);
+			CUDA_OK(m, cudaGetLastError());
+			return LOCO_OK;
+		}
 		if (bucket) {
 			// single-pass fixed-capacity buckets: chunks of ~4M queries, at least 32 per leaf on average
 			int64_t chunk = m->opt_chunk > 0 ? m->opt_chunk : std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 32);
@@ -377,7 +385,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
 				const int64_t n = std::min(chunk, Q - o);
 				m->launches += launch_eval_scalar_bucket_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, bw[k], m->sm_count, m->opt_fp32 != 0, used[k]++,
-				                                               run_on[k]);
+				                                               run_on[k], deriv_dir);
 			}
 			if (ns > 1)
 				for (int j = 0; j < ns; j++) { CUDA_OK(m, cudaEventRecord(m->ev_join[j], m->aux[j])); CUDA_OK(m, cudaStreamWaitEvent(st, m->ev_join[j], 0)); }
@@ -806,9 +814,7 @@ int loco_eval_deriv_batch_device(loco_model_t *m, const double *q, int64_t Q, in
 	if (direction < 0 || direction >= m->flat.N) return fail(m, LOCO_ERR_RANGE, "derivative direction out of range");
 	NEED_DEVICE(m);
 	CUDA_OK(m, cudaSetDevice(m->device));
-	m->launches += launch_eval_deriv_direct(m->dm, q, Q, direction, out, leaf, status, (cudaStream_t)cuda_stream);
-	CUDA_OK(m, cudaGetLastError());
-	return LOCO_OK;
+	return eval_device(m, m->ws[0], (cudaStream_t)cuda_stream, false, q, Q, out, 1, leaf, status, direction);
 }
 
 int loco_eval_deriv_batch(loco_model_t *m, const double *q, int64_t Q, int32_t direction, double *out, int32_t *leaf, uint8_t *status)
@@ -831,8 +837,7 @@ int loco_eval_deriv_batch(loco_model_t *m, const double *q, int64_t Q, int32_t d
 		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
 		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
 		CUDA_OK(m, cudaMemcpyAsync(w.q, q + o * dm.N, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
-		m->launches += launch_eval_deriv_direct(dm, (const double *)w.q, n, direction, (double *)w.out, (int32_t *)w.leaf, (uint8_t *)w.status, w.stream);
-		CUDA_OK(m, cudaGetLastError());
+		if ((rc = eval_device(m, w, w.stream, false, (const double *)w.q, n, (double *)w.out, 1, (int32_t *)w.leaf, (uint8_t *)w.status, direction))) return rc;
 		CUDA_OK(m, cudaMemcpyAsync(out + o, w.out, (size_t)n * 8, cudaMemcpyDeviceToHost, w.stream));
 		if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
 		if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));

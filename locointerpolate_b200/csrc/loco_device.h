@@ -201,6 +201,6 @@ size_t bucket_work_bytes(const DeviceModel &m, int64_t chunk);
 BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base);
 int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t st);
 int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const BucketWork &w,
-                                    int sm_count, bool fp32, int parity, cudaStream_t st);
+                                    int sm_count, bool fp32, int parity, cudaStream_t st, int deriv_dir = -1);
 
 } // namespace loco

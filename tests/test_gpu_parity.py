@@ -186,13 +186,15 @@ def test_derivative_golden_vectors(golden, name):
     m = capi.Model.from_proto(pb, device=0)
     orc = oracleapi.Oracle(protoschema.read_binary(pb))
     for d in range(m.N):
-        out, leaf, status = m.eval_deriv(z["q"], d)
         o_out, o_leaf, o_status, scale = orc.eval_deriv(z["q"], d)
-        assert np.array_equal(leaf, z["leaf"]) and np.array_equal(status, z["status"])
-        ok = status == 0
-        assert_values_close(out[ok], ref[d][ok], scale[ok])
-        assert_values_close(out[ok], o_out[ok], scale[ok])
-        assert np.isnan(out[~ok]).all()
+        for path in (1, 5):  # thread per query; leaf buckets with the derivative factor (cubic tensor-product leaves, else falls back)
+            m.set_option("path", path)
+            out, leaf, status = m.eval_deriv(z["q"], d)
+            assert np.array_equal(leaf, z["leaf"]) and np.array_equal(status, z["status"])
+            ok = status == 0
+            assert_values_close(out[ok], ref[d][ok], scale[ok])
+            assert_values_close(out[ok], o_out[ok], scale[ok])
+            assert np.isnan(out[~ok]).all()
     with pytest.raises(capi.LocoError):
         m.eval_deriv(z["q"], m.N)
 
@@ -241,6 +243,48 @@ def test_locate_grid_equals_descent_bootstrap(N, basis, level):
     _, leaf1, status1 = m.eval(q)
     assert np.array_equal(leaf0, leaf1) and np.array_equal(status0, status1)
     assert leaf1.max() == m.L - 1
+
+
+@pytest.mark.parametrize("N,level,corners", [(3, 4, True), (2, 6, False), (4, 2, True)])
+def test_derivative_throughput_path_equals_direct(N, level, corners):
+    """evalDeriv on cubic tensor-product leaves through the leaf-bucket path (one derivative factor in the contraction)
+    against the thread-per-query term-list kernel, at a batch size where the automatic dispatch picks the buckets; a
+    skewed part of the batch overflows its buckets."""
+    torch = _torch()
+
+    def f(p):
+        return 1 + np.sin(3 * p + np.arange(len(p))).sum()
+    m = capi.Model.bootstrap(N, capi.CUBIC, level, 1, corners, fn=f, device=0)
+    Q = 600_000
+    tq = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(17)) * 1.000002 - 0.000001
+    tq[:100_000] = tq[:100_000] * 0.05 + 0.3  # concentrated in a few leaves
+    tq[100_000:100_040, 0] = 1.5               # outside
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for path in (1, 0, 5):
+        m.set_option("path", path)
+        for d in (0, N - 1):
+            out = torch.empty(Q, dtype=torch.float64, device="cuda")
+            leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+            status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+            m.eval_deriv_device(tq.data_ptr(), Q, d, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+            torch.cuda.synchronize()
+            res[(path, d)] = (out.cpu().numpy(), leaf.cpu().numpy(), status.cpu().numpy())
+    for d in (0, N - 1):
+        a = res[(1, d)]
+        assert (a[2] != 0).sum() >= 40 and np.abs(a[0][a[2] == 0]).max() > 0.1
+        for path in (0, 5):
+            b = res[(path, d)]
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+            ok = a[2] == 0
+            assert np.isnan(b[0][~ok]).all()
+            assert np.abs(a[0][ok] - b[0][ok]).max() <= 1e-12 * max(1.0, np.abs(a[0][ok]).max())
+    # the bucket kernels really ran for path 5
+    m.set_option("path", 5)
+    m.profile_begin()
+    m.eval_deriv_device(tq.data_ptr(), Q, 0, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+    prof = m.profile_end()
+    assert "bucket_eval" in prof and "bucket_scatter" in prof, prof
 
 
 @pytest.mark.parametrize("N,level", [(9, 1), (10, 0), (12, 0)])
