@@ -353,7 +353,9 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool tiles = !in_cube && m->opt_path == 2;
 		const bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256)) &&
 		                    (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE);
-		if (deriv_dir >= 0 && !bucket) {
+		// derivatives on generic leaves with the cubic basis: the sorted path with the derivative factor in its term lists
+		const bool sorted_deriv = deriv_dir >= 0 && !bucket && sorted && dm.basis == CUBIC_BSPLINE && dm.tensor_F == 0;
+		if (deriv_dir >= 0 && !bucket && !sorted_deriv) {
 			// derivatives outside the bucket path (linear basis, generic leaves, small batches): one thread per query
 			m->launches += launch_eval_deriv_direct(dm, q, Q, deriv_dir, out, leaf, status, st);
 			CUDA_OK(m, cudaGetLastError());
@@ -415,7 +417,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 			int k = 0;
 			for (int64_t o = 0; o < Q; o += chunk, k = (k + 1) % ns) {
 				const int64_t n = std::min(chunk, Q - o);
-				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw[k], m->sm_count, m->opt_fp32 != 0, run_on[k]);
+				m->launches += launch_eval_scalar_sorted_chunk(dm, q + o * dm.N, n, out + o, leaf + o, status + o, sw[k], m->sm_count, m->opt_fp32 != 0, run_on[k], deriv_dir);
 			}
 			if (ns > 1) {
 				// join: the caller's stream continues when all of them are done

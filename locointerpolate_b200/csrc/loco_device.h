@@ -185,7 +185,7 @@ size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk);
 SortedWork carve_sorted_work(const DeviceModel &m, void *base);
 int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t st);
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
-                                    int sm_count, bool fp32, cudaStream_t st);
+                                    int sm_count, bool fp32, cudaStream_t st, int deriv_dir = -1);
 
 // ---- single-pass fixed-capacity leaf buckets (loco_bucket.cu)
 struct BucketWork {

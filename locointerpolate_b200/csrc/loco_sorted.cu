@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(256) sorted_scatter_kernel(DeviceModel m, cons
 // Persistent threads: thread t evaluates records t, t+T, t+2T, ...  While record i is being evaluated, record i+T is
 // already in registers with the lines of ITS leaf block on their way into L1, and the load of record i+2T is in flight:
 // the two dependent memory round trips of a query (record -> leaf block) overlap the arithmetic of its predecessors.
-template <int NT, bool CUBIC, bool EXACT, bool TENSOR, bool FP32>
+// DERIV (generic leaves, cubic basis): LCSampledFunction::evalDeriv along cube direction `dir` — the same term lists with
+// LCCubicBSpline::evalDeriv's factor in that dimension (a term that is identically zero in an evaluation cell has a zero derivative there too).
+template <int NT, bool CUBIC, bool EXACT, bool TENSOR, bool FP32, bool DERIV = false>
 __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_kernel(DeviceModel m, const double *__restrict__ xs, const int32_t *__restrict__ cursor,
-                                                           double *__restrict__ out)
+                                                           double *__restrict__ out, int dir = -1)
 {
 	const int N = NT > 0 ? NT : m.N;
 	constexpr int RSmax = rec_doubles(NT > 0 ? NT : kMaxN);
@@ -271,15 +273,19 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 		} else {
 			// LCSample::getInterpolationWeight / newFromWeightedSum over the leaf's term list, as in eval_scalar_direct_kernel,
 			// with weight_ * val pre-multiplied per term (term_wv)
+			auto term = [&](const double *cs, double wv) {
+				if constexpr (DERIV) return term_deriv<NT, CUBIC, EXACT>(cs, wv, x, dir, N);
+				else return term_value<NT, CUBIC, EXACT>(cs, wv, x, N);
+			};
 			if (m.ecell_off) {  // `leaf` is the evaluation cell: only the merged terms that reach this part of the leaf
 				for (int t = __ldg(m.eterm_off + leaf), t1 = __ldg(m.eterm_off + leaf + 1); t < t1; t++)
-					r += term_value<NT, CUBIC, EXACT>(m.eterm_cs + (int64_t)t * 2 * N, __ldg(m.eterm_wv + t), x, N);
+					r += term(m.eterm_cs + (int64_t)t * 2 * N, __ldg(m.eterm_wv + t));
 			} else if (m.mterm_off) {  // merged: one term per distinct basis function of the leaf
 				for (int t = __ldg(m.mterm_off + leaf), t1 = __ldg(m.mterm_off + leaf + 1); t < t1; t++)
-					r += term_value<NT, CUBIC, EXACT>(m.mterm_cs + (int64_t)t * 2 * N, __ldg(m.mterm_wv + t), x, N);
+					r += term(m.mterm_cs + (int64_t)t * 2 * N, __ldg(m.mterm_wv + t));
 			} else {
 				for (int t = __ldg(m.term_off + leaf), t1 = __ldg(m.term_off + leaf + 1); t < t1; t++)
-					r += term_value<NT, CUBIC, EXACT>(m.term_cs + (int64_t)t * 2 * N, __ldg(m.term_wv + t), x, N);
+					r += term(m.term_cs + (int64_t)t * 2 * N, __ldg(m.term_wv + t));
 			}
 		}
 		out[qi] = r;
@@ -301,10 +307,13 @@ void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t
 	sorted_scatter_kernel<NT><<<(unsigned)((Q + 256 * kScatterItems - 1) / (256 * kScatterItems)), 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
 }
 template <int NT, bool CUBIC, bool EXACT>
-void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, bool fp32, cudaStream_t st)
+void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, bool fp32, int deriv_dir, cudaStream_t st)
 {
 	const unsigned g = (unsigned)std::min<int64_t>((Q + 255) / 256, (int64_t)sm_count * 8);
 	LOCO_KERNEL("sorted_eval", st);
+	if constexpr (CUBIC) {
+		if (deriv_dir >= 0) { sorted_eval_kernel<NT, true, EXACT, false, false, true><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out, deriv_dir); return; }
+	}
 	if constexpr (NT > 0) {
 		if (m.tensor_F > 0 && fp32 && m.tl_vals_f32) { sorted_eval_kernel<NT, CUBIC, EXACT, true, true><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
 		if (m.tensor_F > 0) { sorted_eval_kernel<NT, CUBIC, EXACT, true, false><<<g, 256, 0, st>>>(m, w.xs, w.cursor, out); return; }
@@ -339,8 +348,9 @@ int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t 
 	return 0;
 }
 
+// deriv_dir >= 0: derivatives along that cube direction; callers guarantee a cubic basis and generic (non-tensor) leaves
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
-                                    int sm_count, bool fp32, cudaStream_t st)
+                                    int sm_count, bool fp32, cudaStream_t st, int deriv_dir)
 {
 	static const bool scan_smem_set = [] {
 		cudaFuncSetAttribute(sorted_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kScanSeg + kScanSeg / 32) * sizeof(int)));
@@ -353,8 +363,8 @@ int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64
 	case NT:                                                                                                 \
 		run_count<NT>(m, q, Q, leaf, status, out, w, st);                                                    \
 		run_scatter<NT>(m, q, Q, leaf, status, w, st);                                                       \
-		if (cubic) { if (exact) run_eval<NT, true, true>(m, Q, w, out, sm_count, fp32, st); else run_eval<NT, true, false>(m, Q, w, out, sm_count, fp32, st); } \
-		else { if (exact) run_eval<NT, false, true>(m, Q, w, out, sm_count, fp32, st); else run_eval<NT, false, false>(m, Q, w, out, sm_count, fp32, st); }     \
+		if (cubic) { if (exact) run_eval<NT, true, true>(m, Q, w, out, sm_count, fp32, deriv_dir, st); else run_eval<NT, true, false>(m, Q, w, out, sm_count, fp32, deriv_dir, st); } \
+		else { if (exact) run_eval<NT, false, true>(m, Q, w, out, sm_count, fp32, deriv_dir, st); else run_eval<NT, false, false>(m, Q, w, out, sm_count, fp32, deriv_dir, st); }     \
 		break;
 	switch (m.N <= kMaxTemplateN ? m.N : 0) {
 		LOCO_SCASE(0) LOCO_SCASE(1) LOCO_SCASE(2) LOCO_SCASE(3) LOCO_SCASE(4) LOCO_SCASE(5) LOCO_SCASE(6) LOCO_SCASE(7) LOCO_SCASE(8)

@@ -187,7 +187,7 @@ def test_derivative_golden_vectors(golden, name):
     orc = oracleapi.Oracle(protoschema.read_binary(pb))
     for d in range(m.N):
         o_out, o_leaf, o_status, scale = orc.eval_deriv(z["q"], d)
-        for path in (1, 5):  # thread per query; leaf buckets with the derivative factor (cubic tensor-product leaves, else falls back)
+        for path in (1, 5, 4):  # thread per query; leaf buckets / sorted term lists with the derivative factor (cubic basis, else falls back)
             m.set_option("path", path)
             out, leaf, status = m.eval_deriv(z["q"], d)
             assert np.array_equal(leaf, z["leaf"]) and np.array_equal(status, z["status"])
@@ -285,6 +285,42 @@ def test_derivative_throughput_path_equals_direct(N, level, corners):
     m.eval_deriv_device(tq.data_ptr(), Q, 0, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
     prof = m.profile_end()
     assert "bucket_eval" in prof and "bucket_scatter" in prof, prof
+
+
+def test_derivative_on_adaptive_tree_sorted_path(golden):
+    """evalDeriv on the reference's TestDebug tree (generic leaves, cubic): sorted path keyed by evaluation cell with the
+    derivative factor in the cells' term lists, against the thread-per-query kernel and the reference's own derivatives."""
+    torch = _torch()
+    pb, z = golden("cub2d_testdebug")
+    m = capi.Model.from_proto(pb, device=0)
+    ref = np.load(os.path.join(GOLDEN, "cub2d_testdebug.deriv.npz"))["deriv"]
+    Q = 1_000_000
+    tq = torch.rand((Q, 2), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(23))
+    tq[:len(z["q"])] = torch.from_numpy(z["q"]).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    for path in (1, 0):
+        m.set_option("path", path)
+        for d in (0, 1):
+            out = torch.empty(Q, dtype=torch.float64, device="cuda")
+            leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+            status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+            m.eval_deriv_device(tq.data_ptr(), Q, d, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+            torch.cuda.synchronize()
+            res[(path, d)] = (out.cpu().numpy(), leaf.cpu().numpy(), status.cpu().numpy())
+    nz = len(z["q"])
+    for d in (0, 1):
+        a, b = res[(1, d)], res[(0, d)]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        ok = a[2] == 0
+        assert np.abs(a[0][ok] - b[0][ok]).max() <= 1e-11 * np.abs(a[0][ok]).max()
+        okz = z["status"] == 0
+        assert np.array_equal(b[1][:nz], z["leaf"]) and np.array_equal(b[2][:nz], z["status"])
+        assert np.abs(b[0][:nz][okz] - ref[d][okz]).max() <= 1e-11 * np.abs(ref[d][okz]).max()
+    m.set_option("path", 0)
+    m.profile_begin()
+    m.eval_deriv_device(tq.data_ptr(), Q, 0, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+    assert "sorted_eval" in m.profile_end()
 
 
 @pytest.mark.parametrize("N,level", [(9, 1), (10, 0), (12, 0)])

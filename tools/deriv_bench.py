@@ -1,5 +1,6 @@
 """Throughput of the batched evalDeriv on the c2 model (3-D cubic, bootstrap 5, 32,768 leaves):
-thread-per-query term-list kernel (path 1) against the leaf-bucket path with the derivative factor (automatic dispatch).
+thread-per-query term-list kernel (path 1) against the throughput path with the derivative factor (automatic dispatch:
+leaf buckets on tensor-product leaves, sorted term lists keyed by evaluation cell on the adaptive tree of --adaptive).
 
     python tools/deriv_bench.py [--queries 100000000]
 """
@@ -18,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--level", type=int, default=5)
+    ap.add_argument("--adaptive", action="store_true", help="the TestDebug adaptive tree instead of the c2 bootstrap grid")
     args = ap.parse_args()
     import torch
     from locointerpolate_b200 import capi
@@ -25,7 +27,16 @@ def main():
 
     def f(p):
         return 1 + np.sin(3 * p + np.arange(len(p))).sum()
-    m = capi.Model.bootstrap(N, capi.CUBIC, args.level, 1, True, fn=f, device=0)
+    if args.adaptive:  # the reference's TestDebug tree (generic leaves): sorted path keyed by evaluation cell
+        import gzip
+        import tempfile
+        N = 2
+        with tempfile.NamedTemporaryFile(suffix=".pb", delete=False) as t:
+            t.write(gzip.open(os.path.join(ROOT, "tests", "golden", "cub2d_testdebug.pb.gz"), "rb").read())
+        m = capi.Model.from_proto(t.name, device=0)
+        os.unlink(t.name)
+    else:
+        m = capi.Model.bootstrap(N, capi.CUBIC, args.level, 1, True, fn=f, device=0)
     q = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
     out = torch.empty(Q, dtype=torch.float64, device="cuda")
     leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
@@ -33,7 +44,7 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     res = {}
     ref = None
-    for path, name in ((1, "direct"), (0, "buckets")):
+    for path, name in ((1, "direct"), (0, "throughput_path")):
         m.set_option("path", path)
         for _ in range(2):
             m.eval_deriv_device(q.data_ptr(), Q, 1, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
