@@ -133,6 +133,18 @@ int loco_support_set(const loco_model_t *m, int32_t leaf, int32_t *ids, int32_t 
 /* LCSampledFunction::getMinRange/getMaxRange (LCSampledFunction.cpp:52-59): ranges [2N] = min,max per parameter */
 int loco_model_domain(const loco_model_t *m, double *ranges);
 
+/* Introspection of the compacted term lists of a scalar model on generic leaves (no reference counterpart: the lists are
+ * derived data, see DESIGN.md "merged terms" and "evaluation cells"; available on handles created with LOCO_HOST_ONLY,
+ * device handles release the host copies after upload).
+ * loco_merged_terms: the distinct basis functions of a leaf after merging equal (centre, support) pairs over its influencing
+ *   samples (LCBasisFunctionKey equality, LCBasisFunction.h:85-104): centre[n*N], support[n*N]; *first_id = index of the
+ *   leaf's first merged term in the model-wide numbering used by loco_eval_cell_terms.
+ * loco_eval_cells: the leaf's sub-grid, 2^bits[d] cells per dimension (dimension 0 fastest), cells first_cell .. first_cell+n_cells-1.
+ * loco_eval_cell_terms: model-wide merged-term ids listed for one evaluation cell. */
+int loco_merged_terms(const loco_model_t *m, int32_t leaf, double *centre, double *support, int32_t cap, int32_t *n, int64_t *first_id);
+int loco_eval_cells(const loco_model_t *m, int32_t leaf, int32_t *bits, int64_t *first_cell, int64_t *n_cells);
+int loco_eval_cell_terms(const loco_model_t *m, int64_t cell, int64_t *term_ids, int32_t cap, int32_t *n);
+
 /* LCAdaptiveGridCell::ranges_ of a leaf in cube coordinates: box [2N] = lo,hi per dimension (LCAdaptiveGridCell.h:89) */
 int loco_leaf_box(const loco_model_t *m, int32_t leaf, double *box);
 

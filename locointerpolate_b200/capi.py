@@ -71,6 +71,9 @@ SIGNATURES = {
     "loco_eval_batch_ring_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "loco_model_domain": (C.c_int, [_vp, _vp]),
     "loco_leaf_box": (C.c_int, [_vp, _i32, _vp]),
+    "loco_merged_terms": (C.c_int, [_vp, _i32, _vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_i64)]),
+    "loco_eval_cells": (C.c_int, [_vp, _i32, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "loco_eval_cell_terms": (C.c_int, [_vp, _i64, _vp, _i32, C.POINTER(_i32)]),
     "loco_eval_deriv_batch": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "loco_eval_deriv_batch_device": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "loco_error_check": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, C.POINTER(_i64)]),
@@ -361,6 +364,31 @@ class Model:
         r = np.empty(2 * self.N)
         self._check(lib().loco_leaf_box(self._h, leaf, _ptr(r)))
         return r.reshape(self.N, 2)
+
+    # ---- compacted term lists (introspection; host-only handles)
+    def merged_terms(self, leaf: int):
+        """(centre [n, N], support [n, N], first_id) of the leaf's merged basis functions"""
+        n, first = _i32(), _i64()
+        self._check(lib().loco_merged_terms(self._h, leaf, None, None, 0, C.byref(n), C.byref(first)))
+        c, s = np.empty((n.value, self.N)), np.empty((n.value, self.N))
+        if n.value:
+            self._check(lib().loco_merged_terms(self._h, leaf, _ptr(c), _ptr(s), n.value, C.byref(n), C.byref(first)))
+        return c, s, first.value
+
+    def eval_cells(self, leaf: int):
+        """(bits [N], first_cell, n_cells) of the leaf's evaluation sub-grid"""
+        bits = np.zeros(self.N, dtype=np.int32)
+        first, cnt = _i64(), _i64()
+        self._check(lib().loco_eval_cells(self._h, leaf, _ptr(bits), C.byref(first), C.byref(cnt)))
+        return bits, first.value, cnt.value
+
+    def eval_cell_terms(self, cell: int) -> np.ndarray:
+        n = _i32()
+        self._check(lib().loco_eval_cell_terms(self._h, cell, None, 0, C.byref(n)))
+        ids = np.empty(n.value, dtype=np.int64)
+        if n.value:
+            self._check(lib().loco_eval_cell_terms(self._h, cell, _ptr(ids), n.value, C.byref(n)))
+        return ids
 
     # ---- error check
     def error_check(self, q, truth, threshold: float):

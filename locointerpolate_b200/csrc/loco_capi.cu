@@ -648,6 +648,54 @@ int loco_support_set(const loco_model_t *m, int32_t leaf, int32_t *ids, int32_t 
 	return LOCO_OK;
 }
 
+int loco_merged_terms(const loco_model_t *m, int32_t leaf, double *centre, double *support, int32_t cap, int32_t *n, int64_t *first_id)
+{
+	if (!m || !n) return fail(m, LOCO_ERR_INVALID, "null argument");
+	const Flat &f = m->flat;
+	if (leaf < 0 || leaf >= f.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	if (f.mterm_off.empty()) { *n = 0; if (first_id) *first_id = 0; return LOCO_OK; }
+	const int64_t a = f.mterm_off[(size_t)leaf], b = f.mterm_off[(size_t)leaf + 1];
+	*n = (int32_t)(b - a);
+	if (first_id) *first_id = a;
+	if (!centre && !support) return LOCO_OK;
+	if ((int64_t)f.mterm_cs.size() < b * 2 * f.N) return fail(m, LOCO_ERR_INVALID, "term lists were released after upload (use a host-only handle)");
+	if (cap < b - a) return fail(m, LOCO_ERR_RANGE, "term buffer too small");
+	for (int64_t t = a; t < b; t++)
+		for (int i = 0; i < f.N; i++) {
+			const double c = f.mterm_cs[(size_t)t * 2 * f.N + 2 * i], v = f.mterm_cs[(size_t)t * 2 * f.N + 2 * i + 1];
+			if (centre) centre[(t - a) * f.N + i] = c;
+			if (support) support[(t - a) * f.N + i] = f.exact_rcp ? 1.0 / v : v;  // stored as the reciprocal when that is exact
+		}
+	return LOCO_OK;
+}
+
+int loco_eval_cells(const loco_model_t *m, int32_t leaf, int32_t *bits, int64_t *first_cell, int64_t *n_cells)
+{
+	if (!m) return fail(m, LOCO_ERR_INVALID, "null argument");
+	const Flat &f = m->flat;
+	if (leaf < 0 || leaf >= f.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	const bool have = !f.ecell_off.empty();
+	if (bits) for (int i = 0; i < f.N; i++) bits[i] = have ? f.ecell_bits[(size_t)leaf * f.N + i] : 0;
+	if (first_cell) *first_cell = have ? f.ecell_off[(size_t)leaf] : leaf;
+	if (n_cells) *n_cells = have ? f.ecell_off[(size_t)leaf + 1] - f.ecell_off[(size_t)leaf] : 1;
+	return LOCO_OK;
+}
+
+int loco_eval_cell_terms(const loco_model_t *m, int64_t cell, int64_t *term_ids, int32_t cap, int32_t *n)
+{
+	if (!m || !n) return fail(m, LOCO_ERR_INVALID, "null argument");
+	const Flat &f = m->flat;
+	if (f.ecell_off.empty()) return fail(m, LOCO_ERR_INVALID, "the model has no evaluation cells");
+	if (cell < 0 || cell >= f.ecell_off.back()) return fail(m, LOCO_ERR_RANGE, "evaluation cell out of range");
+	const int64_t a = f.eterm_off[(size_t)cell], b = f.eterm_off[(size_t)cell + 1];
+	*n = (int32_t)(b - a);
+	if (!term_ids) return LOCO_OK;
+	if ((int64_t)f.eterm_src.size() < b) return fail(m, LOCO_ERR_INVALID, "term lists were released after upload (use a host-only handle)");
+	if (cap < b - a) return fail(m, LOCO_ERR_RANGE, "term buffer too small");
+	for (int64_t t = a; t < b; t++) term_ids[t - a] = f.eterm_src[(size_t)t];
+	return LOCO_OK;
+}
+
 int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, int32_t *n_border)
 {
 	if (!m) return fail(m, LOCO_ERR_INVALID, "null argument");
