@@ -433,6 +433,46 @@ public:
 		return LCError();
 	}
 
+	// One level-synchronous pass of adaptiveSample (LCAdaptiveGrid.cpp:481-545) for ANY sampled function, e.g. one wrapped
+	// around a grid the caller refines itself: decideSplit for all leaves in one batch (CENTER_BASED, :594-602), then the
+	// flagged leaves of the largest size class below maxLevel (what the reference's size-ordered heap would pop next) with
+	// the cyclic direction rule (:553 generalised to N parameters: the first dimension of largest extent), in DESCENDING leaf
+	// order so that splitting one of them (leaves are numbered depth-first, child1 first) leaves the others' indices valid.
+	// The caller performs refineCell on its own grid for every request and re-flattens.
+	struct SplitRequest { int32_t leaf; int direction; };
+	static LCError selectSplits(LCSampledFunction *fn, double threshold, int maxLevel, std::vector<SplitRequest> *requests,
+	                            std::vector<double> *errMax = nullptr)
+	{
+		requests->clear();
+		if (!fn || !fn->handle()) return LCError("no model attached");
+		loco_model_t *m = fn->handle();
+		const int64_t L = fn->getNLeaves();
+		const int N = fn->getNParams();
+		std::vector<double> err((size_t)L), volume((size_t)L), box((size_t)2 * N);
+		std::vector<uint8_t> split((size_t)L);
+		std::vector<int> level((size_t)L), dir((size_t)L);
+		if (loco_center_error(m, threshold, err.data(), split.data())) return loco_detail::last_error(m);
+		double top = 0;
+		for (int64_t l = 0; l < L; l++) {
+			if (loco_leaf_box(m, (int32_t)l, box.data())) return loco_detail::last_error(m);
+			double vol = 1, lv = 0, widest = -1;
+			for (int d = 0; d < N; d++) {
+				const double w = box[2 * d + 1] - box[2 * d];
+				vol *= w;
+				lv += std::log2(2.0 / w);
+				if (w > widest) { widest = w; dir[(size_t)l] = d; }
+			}
+			volume[(size_t)l] = vol;
+			level[(size_t)l] = (int)std::lround(lv);
+			if (split[(size_t)l] && level[(size_t)l] < maxLevel) top = std::max(top, vol);
+		}
+		for (int64_t l = L - 1; l >= 0; l--)
+			if (split[(size_t)l] && level[(size_t)l] < maxLevel && volume[(size_t)l] >= top * (1 - 1e-12))
+				requests->push_back(SplitRequest{(int32_t)l, dir[(size_t)l]});
+		if (errMax) *errMax = std::move(err);
+		return LCError();
+	}
+
 private:
 	static void trampoline(const double *p, double *out, void *user)
 	{

@@ -218,6 +218,19 @@ static void functionApproximationTest(double thr, int maxDepth, int boot)
 	const bool mayRefine = 2 * boot < maxDepth;
 	for (size_t l = 0; consistent && l < split.size(); l++) consistent = split[l] == (mayRefine && !((err[l] - thr) <= 0) ? 1 : 0);
 	CHECK(consistent, "split[l] == (level < maxTreeDepth && !(err - threshold <= 0))");
+	// the pass selection of the level-synchronous refinement loop: all leaves of a bootstrap grid have one size, so the
+	// requests are exactly the flagged leaves, in descending order, each along dimension 0 (square cells: first widest)
+	std::vector<LCAdaptiveGrid::SplitRequest> req;
+	std::vector<double> err3;
+	CHECK(LCAdaptiveGrid::selectSplits(grid.getSampledFunction(), thr, maxDepth, &req, &err3).isOK(), "selectSplits");
+	size_t flagged = 0;
+	for (size_t l = 0; l < split.size(); l++) flagged += split[l] ? 1 : 0;
+	bool sel = req.size() == flagged && err3.size() == err.size();
+	for (size_t i = 0; sel && i < req.size(); i++)
+		sel = split[(size_t)req[i].leaf] == 1 && req[i].direction == 0 && (i == 0 || req[i].leaf < req[i - 1].leaf);
+	for (size_t l = 0; sel && l < err.size(); l++) sel = err3[l] == err[l];
+	CHECK(sel, "selectSplits returns the flagged leaves of the largest size class, descending, cyclic direction");
+	CHECK(LCAdaptiveGrid::selectSplits(grid.getSampledFunction(), thr, 2 * boot, &req).isOK() && req.empty(), "no requests at the level limit");
 	LCAdaptiveSamplingParams rnd(maxDepth + 4, thr, boot, 8, LCAdaptiveSamplingParams::ERROR_BASED, LCAdaptiveSamplingParams::RANDOM_SAMPLES);
 	LCAdaptiveGrid grid2(&f, LCBasisFunction::CUBIC_BSPLINE, &rnd, true);
 	std::vector<uint8_t> split2;
