@@ -120,6 +120,39 @@ def test_proto_errors_use_reference_messages(tmp_path):
     assert "sample does not have id" in e.value.msg
 
 
+def test_corrupted_proto_files_never_crash_the_loader(tmp_path):
+    """Truncated / bit-flipped / spliced files must either load (the damage hit a value) or fail with an LCError-style
+    message — the loader validates every length and index it reads (loco_proto.cpp, validate_graph)."""
+    import random
+    src = open(os.path.join(ROOT, "tests", "golden", "cub2d_boot1_adapt.pb"), "rb").read()
+    rnd = random.Random(11)
+    outcomes = {"ok": 0, "err": 0}
+    for it in range(120):
+        b = bytearray(src)
+        mode = rnd.choice(["trunc", "flip", "flip", "insert", "zero"])
+        if mode == "trunc":
+            b = b[:rnd.randrange(0, len(b))]
+        elif mode == "flip":
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        elif mode == "insert":
+            i = rnd.randrange(len(b))
+            b[i:i] = bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 9)))
+        else:
+            i, n = rnd.randrange(len(b)), rnd.randrange(1, 64)
+            b[i:i + n] = bytes(n)
+        path = str(tmp_path / "damaged.pb")
+        open(path, "wb").write(bytes(b))
+        try:
+            m = capi.Model.from_proto(path, device=capi.HOST_ONLY)
+            assert m.L >= 1
+            outcomes["ok"] += 1
+        except capi.LocoError as e:
+            assert str(e)
+            outcomes["err"] += 1
+    assert outcomes["err"] > 20 and outcomes["ok"] + outcomes["err"] == 120
+
+
 def test_packed_doubles_are_accepted(tmp_path):
     """proto3-style writers pack repeated doubles; the reader must take both encodings."""
     g = protoschema.read_binary(os.path.join(ROOT, "tests", "golden", "cub2d_boot2.pb"))
