@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--level", type=int, default=-1, help="override the workload's bootstrap level (experiments)")
     ap.add_argument("--queries", type=int, default=0, help="queries per step per GPU (default: the workload's)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (default: sized for ~10-20 s)")
+    ap.add_argument("--ecell-poly", type=int, default=0, help="1: polynomial form of the evaluation cells (adaptive scalar trees; option ecell_poly)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--gather", default="rotate", choices=["rotate", "all"],
@@ -289,6 +290,8 @@ def measure(name, w, args, rank, world, local, config, full):
     m, amp, phase = build_model(capi, w, local)
     m.set_option("path", args.path)
     m.set_option("chunk", args.chunk)
+    if args.ecell_poly:
+        m.set_option("ecell_poly", args.ecell_poly)
     if args.overlap:
         m.set_option("overlap", args.overlap)
     info = m.info

@@ -95,6 +95,7 @@ typedef struct loco_info {
 	int64_t n_fold_entries;  /* value rows over all tensor leaves after folding samples that share a value object (0: no tensor leaves) */
 	int64_t n_eval_cells;    /* evaluation cells of the sorted scalar path (0: sorted by leaf) */
 	int64_t n_eval_terms;    /* term-list entries over all evaluation cells */
+	int64_t n_poly_cells;    /* evaluation cells that have a single-polynomial form */
 } loco_info_t;
 
 /* f : original parameter space [N] -> value [D]   (LCFunction::evalShapeInfo, LCFunction/LCFunction.h:32) */
@@ -144,6 +145,11 @@ int loco_model_domain(const loco_model_t *m, double *ranges);
 int loco_merged_terms(const loco_model_t *m, int32_t leaf, double *centre, double *support, int32_t cap, int32_t *n, int64_t *first_id);
 int loco_eval_cells(const loco_model_t *m, int32_t leaf, int32_t *bits, int64_t *first_cell, int64_t *n_cells);
 int loco_eval_cell_terms(const loco_model_t *m, int64_t cell, int64_t *term_ids, int32_t cap, int32_t *n);
+/* polynomial form of an evaluation cell (SURVEY 8f.4 applied per cell, csrc/loco_cellpoly.h): *n_coef = F^N (0: the cell keeps
+ * its term list), geom [2N] = mid_d, 1/halfwidth_d, coef [F^N] with dimension 0 fastest: value(x) = sum_j coef[j] prod_d t_d^(j_d),
+ * t_d = (x_d - mid_d) * geom[2d+1] in cube coordinates.  Computed on the host from the handle's current values with the
+ * same code the device kernel runs (host-only handles, scalar functions). */
+int loco_eval_cell_poly(const loco_model_t *m, int64_t cell, double *geom, double *coef, int32_t cap, int32_t *n_coef);
 
 /* LCAdaptiveGridCell::ranges_ of a leaf in cube coordinates: box [2N] = lo,hi per dimension (LCAdaptiveGridCell.h:89) */
 int loco_leaf_box(const loco_model_t *m, int32_t leaf, double *box);
@@ -236,7 +242,9 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
  *          "uniform" 1 (default): cubic tensor leaves with equally spaced centres form their four factors per dimension from one parameter;
  *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0);
  *          "ecells" 1 (default): path 4 on generic leaves sorts by evaluation cell (a regular sub-grid of the leaves with many terms,
- *                 each cell listing only the basis functions that reach it) | 0 by leaf */
+ *                 each cell listing only the basis functions that reach it) | 0 by leaf;
+ *          "ecell_poly" 1: evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
+ *                 (changes the summation order, within the 1e-12 bar) | 0 (default in this round): always the term list */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);

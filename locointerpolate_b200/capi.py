@@ -44,7 +44,7 @@ class _GraphStruct(C.Structure):
 class _Info(C.Structure):
     _fields_ = [(n, _i32) for n in ("n_params", "value_dim", "basis_type", "exact_rcp", "depth", "max_support", "max_terms", "device")] + \
                [(n, _i64) for n in ("n_samples", "n_value_rows", "n_leaves", "n_cells", "n_border_cells", "n_basis_functions",
-                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries", "n_eval_cells", "n_eval_terms")]
+                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries", "n_eval_cells", "n_eval_terms", "n_poly_cells")]
 
 
 VALUE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp)
@@ -74,6 +74,7 @@ SIGNATURES = {
     "loco_merged_terms": (C.c_int, [_vp, _i32, _vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_i64)]),
     "loco_eval_cells": (C.c_int, [_vp, _i32, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "loco_eval_cell_terms": (C.c_int, [_vp, _i64, _vp, _i32, C.POINTER(_i32)]),
+    "loco_eval_cell_poly": (C.c_int, [_vp, _i64, _vp, _vp, _i32, C.POINTER(_i32)]),
     "loco_eval_deriv_batch": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "loco_eval_deriv_batch_device": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "loco_error_check": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, C.POINTER(_i64)]),
@@ -389,6 +390,16 @@ class Model:
         if n.value:
             self._check(lib().loco_eval_cell_terms(self._h, cell, _ptr(ids), n.value, C.byref(n)))
         return ids
+
+    def eval_cell_poly(self, cell: int):
+        """(geom [N, 2] = mid, 1/halfwidth; coef [F^N], dimension 0 fastest) or None if the cell keeps its term list"""
+        n = _i32()
+        self._check(lib().loco_eval_cell_poly(self._h, cell, None, None, 0, C.byref(n)))
+        if n.value == 0:
+            return None
+        geom, coef = np.empty(2 * self.N), np.empty(n.value)
+        self._check(lib().loco_eval_cell_poly(self._h, cell, _ptr(geom), _ptr(coef), n.value, C.byref(n)))
+        return geom.reshape(self.N, 2), coef
 
     # ---- error check
     def error_check(self, q, truth, threshold: float):

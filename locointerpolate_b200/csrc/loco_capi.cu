@@ -17,6 +17,7 @@
 #include "loco_bootstrap.h"
 #include "loco_device.h"
 #include "loco_flat.h"
+#include "loco_cellpoly.h"
 #include "loco_proto.h"
 
 using namespace loco;
@@ -66,6 +67,9 @@ struct loco_model {
 	double *d_mterm_wv = nullptr;
 	double *d_eterm_wv = nullptr;
 	const int32_t *d_ecell_off = nullptr;
+	const int32_t *d_epoly_idx = nullptr, *d_epoly_cell = nullptr;  // polynomial evaluation cells (option "ecell_poly")
+	double *d_epoly = nullptr;
+	int32_t n_epoly = 0;
 	double *d_tl_block = nullptr;
 	float *d_tl_vals_f32 = nullptr;
 	int64_t n_terms = 0;
@@ -141,6 +145,7 @@ int refresh_term_wv(loco_model *m)
 		m->launches += launch_update_term_wv(m->dm, m->d_term_wv, m->n_terms, nullptr);
 		m->launches += launch_update_mterm_wv(m->dm, m->d_mterm_wv, nullptr);
 		m->launches += launch_update_eterm_wv(m->dm, m->d_eterm_wv, nullptr);
+		m->launches += launch_update_epoly(m->dm, m->d_epoly_cell, m->n_epoly, m->d_epoly, nullptr);
 		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, m->d_tl_vals_f32, nullptr);
 	}
 	CUDA_OK(m, cudaGetLastError());
@@ -207,6 +212,7 @@ int build_device_model(loco_model *m)
 		std::vector<int32_t>().swap(f.mrun_term);
 	}
 	dm.ecell_off = nullptr; dm.eterm_src = nullptr; dm.eterm_wv = nullptr; dm.n_ecells = 0; dm.n_eterms = 0;
+	dm.epoly_idx = nullptr; dm.epoly = nullptr; dm.epoly_stride = 0;
 	if (!f.ecell_off.empty() && dm.mterm_off) {
 		std::vector<int32_t> coff = narrow(m, f.ecell_off, &ok), toff = narrow(m, f.eterm_off, &ok);
 		if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
@@ -222,6 +228,22 @@ int build_device_model(loco_model *m)
 		if ((rc = upload(m, zeros, &dwv))) return rc;
 		m->d_eterm_wv = const_cast<double *>(dwv);
 		dm.eterm_wv = dwv;
+		if (!f.epoly_cell.empty()) {
+			const int F = f.basis == CUBIC_BSPLINE ? 4 : 2;
+			int P = 1;
+			for (int i = 0; i < dm.N; i++) P *= F;
+			dm.epoly_stride = 2 * dm.N + P;
+			m->n_epoly = (int32_t)f.epoly_cell.size();
+			std::vector<double> blocks((size_t)m->n_epoly * dm.epoly_stride, 0.0);
+			for (int32_t i = 0; i < m->n_epoly; i++)
+				std::copy(f.epoly_geom.begin() + (size_t)i * 2 * dm.N, f.epoly_geom.begin() + (size_t)(i + 1) * 2 * dm.N, blocks.begin() + (size_t)i * dm.epoly_stride);
+			const double *dblk = nullptr;
+			if ((rc = upload(m, f.epoly_idx, &m->d_epoly_idx))) return rc;
+			if ((rc = upload(m, f.epoly_cell, &m->d_epoly_cell))) return rc;
+			if ((rc = upload(m, blocks, &dblk))) return rc;
+			m->d_epoly = const_cast<double *>(dblk);
+			dm.epoly = dblk;  // the evaluation uses it only while dm.epoly_idx is set (option "ecell_poly", off by default)
+		}
 		std::vector<double>().swap(f.eterm_cs);
 		std::vector<int32_t>().swap(f.eterm_src);
 	}
@@ -633,6 +655,7 @@ int loco_model_info(const loco_model_t *m, loco_info_t *info)
 	info->n_fold_entries = f.fold_off.empty() ? 0 : f.fold_off.back();
 	info->n_eval_cells = f.ecell_off.empty() ? 0 : f.ecell_off.back();
 	info->n_eval_terms = f.eterm_off.empty() ? 0 : f.eterm_off.back();
+	info->n_poly_cells = (int64_t)f.epoly_cell.size();
 	return LOCO_OK;
 }
 
@@ -693,6 +716,48 @@ int loco_eval_cell_terms(const loco_model_t *m, int64_t cell, int64_t *term_ids,
 	if ((int64_t)f.eterm_src.size() < b) return fail(m, LOCO_ERR_INVALID, "term lists were released after upload (use a host-only handle)");
 	if (cap < b - a) return fail(m, LOCO_ERR_RANGE, "term buffer too small");
 	for (int64_t t = a; t < b; t++) term_ids[t - a] = f.eterm_src[(size_t)t];
+	return LOCO_OK;
+}
+
+int loco_eval_cell_poly(const loco_model_t *m, int64_t cell, double *geom, double *coef, int32_t cap, int32_t *n_coef)
+{
+	if (!m || !n_coef) return fail(m, LOCO_ERR_INVALID, "null argument");
+	const Flat &f = m->flat;
+	if (f.ecell_off.empty()) return fail(m, LOCO_ERR_INVALID, "the model has no evaluation cells");
+	if (cell < 0 || cell >= f.ecell_off.back()) return fail(m, LOCO_ERR_RANGE, "evaluation cell out of range");
+	*n_coef = 0;
+	if (f.epoly_idx.empty() || f.epoly_idx[(size_t)cell] < 0) return LOCO_OK;
+	const int N = f.N;
+	const bool cubic = m->graph.basis == CUBIC_BSPLINE;
+	const int F = cubic ? 4 : 2;
+	int P = 1;
+	for (int i = 0; i < N; i++) P *= F;
+	*n_coef = P;
+	if (!geom && !coef) return LOCO_OK;
+	if (cap < P) return fail(m, LOCO_ERR_RANGE, "coefficient buffer too small");
+	const int64_t a = f.eterm_off[(size_t)cell], b = f.eterm_off[(size_t)cell + 1];
+	if ((int64_t)f.eterm_src.size() < b || f.mrun_term.empty() || f.term_w.empty() || m->graph.values.empty())
+		return fail(m, LOCO_ERR_INVALID, "term lists were released after upload (use a host-only handle)");
+	const double *gm = &f.epoly_geom[(size_t)f.epoly_idx[(size_t)cell] * 2 * N];
+	if (geom) std::copy(gm, gm + 2 * N, geom);
+	if (!coef) return LOCO_OK;
+	std::fill(coef, coef + P, 0.0);
+	double p[8 * 4];
+	for (int64_t t = a; t < b; t++) {
+		const int64_t mt = f.eterm_src[(size_t)t];
+		double wv = 0.0;  // as mterm_wv_kernel: weight * value summed over the merged run
+		for (int64_t e = f.mrun_off[(size_t)mt]; e < f.mrun_off[(size_t)mt + 1]; e++) {
+			const int32_t o = f.mrun_term[(size_t)e];
+			wv += f.term_w[(size_t)o] * m->graph.values[(size_t)f.term_row[(size_t)o] * m->graph.D];
+		}
+		for (int i = 0; i < N; i++) {
+			const double c = f.eterm_cs[(size_t)t * 2 * N + 2 * i], v = f.eterm_cs[(size_t)t * 2 * N + 2 * i + 1];
+			const double sp = f.exact_rcp ? 1.0 / v : v;
+			if (cubic) cell_piece_1d<true>(c, sp, gm[2 * i], 1.0 / gm[2 * i + 1], p + i * F);
+			else cell_piece_1d<false>(c, sp, gm[2 * i], 1.0 / gm[2 * i + 1], p + i * F);
+		}
+		if (cubic) cell_poly_accumulate<4>(N, p, wv, coef); else cell_poly_accumulate<2>(N, p, wv, coef);
+	}
 	return LOCO_OK;
 }
 
@@ -1026,7 +1091,13 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "uniform")) { m->opt_uniform = value; m->dm.tensor_uniform = (m->flat.tensor_uniform && value) ? 1 : 0; return LOCO_OK; }  // 0: four separate factor evaluations
 	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
-	if (!strcmp(name, "ecells")) {  // 0: sorted path keyed by leaf, 1: by evaluation cell where the model has them (default)
+	if (!strcmp(name, "ecell_poly")) {  // 1: polynomial form of the evaluation cells no knot crosses (see loco_cellpoly.h), 0: term lists
+		m->dm.epoly_idx = (value && m->dm.ecell_off) ? m->d_epoly_idx : nullptr;
+		return LOCO_OK;
+	}
+	if (!strcmp(name, "ecells")) {
+		// 0: sorted path keyed by leaf, 1: by evaluation cell where the model has them (default)
+		if (!value) m->dm.epoly_idx = nullptr;  // the polynomial cells are a refinement of the evaluation cells
 		if (m->dm.ecell_off) m->d_ecell_off = m->dm.ecell_off;
 		m->dm.ecell_off = value ? m->d_ecell_off : nullptr;
 		return LOCO_OK;

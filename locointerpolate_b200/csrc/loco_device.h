@@ -46,6 +46,11 @@ struct DeviceModel {
 	const int32_t *eterm_src;
 	int32_t n_ecells;
 	int64_t n_eterms;
+	// polynomial evaluation cells (loco_cellpoly.h).  epoly_idx == nullptr: not built, or switched off (option "ecell_poly").
+	// Block of a cell: [2N geometry: mid_d, 1/halfwidth_d | F^N coefficients, dimension 0 fastest], epoly_stride doubles.
+	const int32_t *epoly_idx;   // [E] block index or -1
+	const double *epoly;
+	int32_t epoly_stride;
 	// derivative-only extra terms of the linear basis (CSR by leaf; see Flat::dterm_*)
 	const int32_t *dterm_off;
 	const double *dterm_cs, *dterm_w;
@@ -148,6 +153,7 @@ SortWork carve_sort_work(const DeviceModel &m, int64_t Q, void *base);
 int launch_update_term_wv(const DeviceModel &m, double *term_wv, int64_t T, cudaStream_t st);
 int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t st);
 int launch_update_eterm_wv(const DeviceModel &m, double *eterm_wv, cudaStream_t st);
+int launch_update_epoly(const DeviceModel &m, const int32_t *epoly_cell, int32_t n_epoly, double *epoly, cudaStream_t st);
 int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);

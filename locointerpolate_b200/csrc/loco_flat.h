@@ -86,6 +86,13 @@ struct Flat {
 	std::vector<double> eterm_cs;      // [sum * 2N]
 	std::vector<int32_t> eterm_src;    // [sum] index of the merged term (for weight * value)
 
+	// polynomial evaluation cells (loco_cellpoly.h): cells no knot of a listed basis function crosses and that do not touch
+	// the root box (where the +-1e-6 band would leave the piece).  The coefficients are formed from the current values
+	// (device: epoly_kernel; host: loco_eval_cell_poly for the tests); here only the selection and the geometry.
+	std::vector<int32_t> epoly_idx;    // [E] index of the cell's polynomial block, -1: term list
+	std::vector<int32_t> epoly_cell;   // [Pc]
+	std::vector<double> epoly_geom;    // [Pc * 2N] mid_d, 1 / halfwidth_d
+
 	// derivative-only extra terms (linear basis; see loco_flatten.cpp): hats outside the leaf that the reference's
 	// LCLinearBSpline::evalDeriv still counts because it compares the SIGNED distance with 1
 	std::vector<int64_t> dterm_off;    // [L+1]

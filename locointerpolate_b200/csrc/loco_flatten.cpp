@@ -9,6 +9,7 @@
 // and then pre-filters each leaf's basis functions to those whose box can reach the leaf (terms that
 // are identically zero on the leaf only ever add +0.0 to LCSample::getInterpolationWeight's sum).
 #include "loco_flat.h"
+#include "loco_cellpoly.h"
 
 #include <algorithm>
 #include <cmath>
@@ -382,6 +383,49 @@ Status flatten(const Graph &g, Flat *out)
 			}
 			if (!any || !ok || f.ecell_off.back() >= (int64_t)0x7fffffff) {
 				f.ecell_off.clear(); f.ecell_bits.clear(); f.eterm_off.clear(); f.eterm_cs.clear(); f.eterm_src.clear();
+			} else {
+				// ---- polynomial cells (loco_cellpoly.h)
+				const int F = cubic ? 4 : 2;
+				int64_t P = 1;
+				for (int i = 0; i < N; i++) P *= F;
+				if (N <= 8 && P <= 64) {
+					f.epoly_idx.assign((size_t)f.ecell_off.back(), -1);
+					const double *rb = &g.tree.ranges[0];  // the root box
+					std::vector<double> clo((size_t)N), chi((size_t)N);
+					for (int64_t l = 0; l < L; l++) {
+						const double *lo = &f.leaf_lo[(size_t)l * N], *hi = &f.leaf_hi[(size_t)l * N];
+						const uint8_t *bits = &f.ecell_bits[(size_t)l * N];
+						const int64_t c0 = f.ecell_off[(size_t)l], c1 = f.ecell_off[(size_t)l + 1];
+						if (c1 - c0 < 2) continue;  // undivided leaves keep their term list
+						for (int64_t c = c0; c < c1; c++) {
+							int64_t r = c - c0;
+							bool good = true;
+							for (int i = 0; i < N; i++) {
+								const int64_t gdim = (int64_t)1 << bits[i], k = r % gdim;
+								r /= gdim;
+								const double h = (hi[i] - lo[i]) / (double)gdim;
+								clo[(size_t)i] = lo[i] + h * (double)k;
+								chi[(size_t)i] = lo[i] + h * (double)(k + 1);
+								if ((k == 0 && lo[i] <= rb[2 * i]) || (k == gdim - 1 && hi[i] >= rb[2 * i + 1])) good = false;  // touches the root box
+							}
+							for (int64_t t = f.eterm_off[(size_t)c]; good && t < f.eterm_off[(size_t)c + 1]; t++)
+								for (int i = 0; i < N && good; i++) {
+									const double cc = f.eterm_cs[(size_t)t * 2 * N + 2 * i], v = f.eterm_cs[(size_t)t * 2 * N + 2 * i + 1];
+									const double sp = f.exact_rcp ? 1.0 / v : v;
+									if (cubic ? knot_inside<true>(cc, sp, clo[(size_t)i], chi[(size_t)i]) : knot_inside<false>(cc, sp, clo[(size_t)i], chi[(size_t)i]))
+										good = false;
+								}
+							if (!good) continue;
+							f.epoly_idx[(size_t)c] = (int32_t)f.epoly_cell.size();
+							f.epoly_cell.push_back((int32_t)c);
+							for (int i = 0; i < N; i++) {
+								f.epoly_geom.push_back(0.5 * (clo[(size_t)i] + chi[(size_t)i]));
+								f.epoly_geom.push_back(2.0 / (chi[(size_t)i] - clo[(size_t)i]));
+							}
+						}
+					}
+					if (f.epoly_cell.empty()) f.epoly_idx.clear();
+				}
 			}
 		}
 	}

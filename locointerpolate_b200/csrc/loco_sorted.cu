@@ -277,7 +277,27 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 				if constexpr (DERIV) return term_deriv<NT, CUBIC, EXACT>(cs, wv, x, dir, N);
 				else return term_value<NT, CUBIC, EXACT>(cs, wv, x, N);
 			};
-			if (m.ecell_off) {  // `leaf` is the evaluation cell: only the merged terms that reach this part of the leaf
+			int32_t pi = -1;
+			if constexpr (!DERIV && NT > 0 && ipow_c(CUBIC ? 4 : 2, NT) <= 64) {
+				if (m.ecell_off && m.epoly_idx) pi = __ldg(m.epoly_idx + leaf);
+			}
+			if (pi >= 0) {
+				// the cell lies inside one polynomial piece of every function that reaches it (loco_cellpoly.h):
+				// powers of the local coordinate per dimension, then the same contraction as a tensor-product leaf
+				if constexpr (!DERIV && NT > 0 && ipow_c(CUBIC ? 4 : 2, NT) <= 64) {
+					constexpr int F = CUBIC ? 4 : 2;
+					const double *blk = m.epoly + (int64_t)pi * m.epoly_stride;
+					double f[NT][F];
+#pragma unroll
+					for (int d = 0; d < NT; d++) {
+						const double t = (x.get(d) - __ldg(blk + 2 * d)) * __ldg(blk + 2 * d + 1);
+						f[d][0] = 1.0;
+						f[d][1] = t;
+						if constexpr (CUBIC) { f[d][2] = t * t; f[d][3] = f[d][2] * t; }
+					}
+					r = TensorContract<NT, F, NT - 1>::run(blk + 2 * NT, f, ipow_c(F, NT) / F);
+				}
+			} else if (m.ecell_off) {  // `leaf` is the evaluation cell: only the merged terms that reach this part of the leaf
 				for (int t = __ldg(m.eterm_off + leaf), t1 = __ldg(m.eterm_off + leaf + 1); t < t1; t++)
 					r += term(m.eterm_cs + (int64_t)t * 2 * N, __ldg(m.eterm_wv + t));
 			} else if (m.mterm_off) {  // merged: one term per distinct basis function of the leaf

@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "loco_basis.cuh"
+#include "loco_cellpoly.h"
 #include "loco_device.h"
 #include "loco_sort.cuh"
 #include "loco_tma.cuh"
@@ -387,6 +388,37 @@ int launch_update_eterm_wv(const DeviceModel &m, double *eterm_wv, cudaStream_t 
 {
 	if (!m.eterm_src || m.n_eterms <= 0) return 0;
 	eterm_wv_kernel<<<(unsigned)((m.n_eterms + 255) / 256), 256, 0, st>>>(m, eterm_wv);
+	return 1;
+}
+
+// coefficients of the polynomial evaluation cells from the current eterm_wv (one thread per cell; runs when values change)
+template <bool CUBIC>
+__global__ void epoly_kernel(DeviceModel m, const int32_t *__restrict__ epoly_cell, int32_t n_epoly, double *__restrict__ epoly)
+{
+	constexpr int F = CUBIC ? 4 : 2;
+	const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pi >= n_epoly) return;
+	const int N = m.N;
+	double *blk = epoly + (int64_t)pi * m.epoly_stride;
+	double coef[64], p[8 * F];
+	int P = 1;
+	for (int d = 0; d < N; d++) P *= F;
+	for (int j = 0; j < P; j++) coef[j] = 0.0;
+	const int32_t cell = epoly_cell[pi];
+	for (int t = m.eterm_off[cell], t1 = m.eterm_off[cell + 1]; t < t1; t++) {
+		for (int d = 0; d < N; d++) {
+			const double c = m.eterm_cs[(int64_t)t * 2 * N + 2 * d], v = m.eterm_cs[(int64_t)t * 2 * N + 2 * d + 1];
+			cell_piece_1d<CUBIC>(c, m.exact_rcp ? 1.0 / v : v, blk[2 * d], 1.0 / blk[2 * d + 1], p + d * F);
+		}
+		cell_poly_accumulate<F>(N, p, m.eterm_wv[t], coef);
+	}
+	for (int j = 0; j < P; j++) blk[2 * N + j] = coef[j];
+}
+int launch_update_epoly(const DeviceModel &m, const int32_t *epoly_cell, int32_t n_epoly, double *epoly, cudaStream_t st)
+{
+	if (!epoly || n_epoly <= 0) return 0;
+	if (m.basis == CUBIC_BSPLINE) epoly_kernel<true><<<(n_epoly + 127) / 128, 128, 0, st>>>(m, epoly_cell, n_epoly, epoly);
+	else epoly_kernel<false><<<(n_epoly + 127) / 128, 128, 0, st>>>(m, epoly_cell, n_epoly, epoly);
 	return 1;
 }
 

@@ -59,3 +59,56 @@ def test_cell_lists_cover_every_nonzero_term(golden, name):
         assert not missing.any(), f"leaf {leaf}: {int(missing.sum())} non-zero terms missing from their cell's list"
         checked += len(x)
     assert checked > 0 and total_listed < total_merged  # the cells do shorten the lists
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cell_polynomials_equal_the_oracle(golden, name):
+    """Polynomial form of the evaluation cells (csrc/loco_cellpoly.h, SURVEY 8f.4 per cell): on a cell that no knot crosses,
+    the F^N coefficients computed by the code the device kernel shares must reproduce the reference restatement's values
+    at random points of the cell within the 1e-12 bar."""
+    import protoschema
+    from conftest import assert_values_close
+    from oracle import oracleapi
+    pb, _ = golden(name)
+    m = capi.Model.from_proto(pb, device=capi.HOST_ONLY)
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    cubic = m.info["basis_type"] == capi.CUBIC
+    F = 4 if cubic else 2
+    n_poly = m.info["n_poly_cells"]
+    if name == "cub2d_testdebug":
+        assert n_poly > 0.5 * m.info["n_eval_cells"], (n_poly, m.info["n_eval_cells"])
+    assert n_poly > 0
+    dom = m.domain.reshape(m.N, 2)
+    rng = np.random.default_rng(41)
+    leaves = range(m.L) if m.L <= 60 else rng.choice(m.L, 60, replace=False)
+    pts, vals, seen = [], [], 0
+    for leaf in leaves:
+        bits, first_cell, n_cells = m.eval_cells(int(leaf))
+        for c in range(n_cells):
+            pc = m.eval_cell_poly(first_cell + c)
+            if pc is None:
+                continue
+            seen += 1
+            if seen % 3:  # a third of the polynomial cells is plenty
+                continue
+            geom, coef = pc
+            assert len(coef) == F ** m.N
+            t = rng.uniform(-1, 1, (8, m.N))
+            t[0] = 1.0   # corners of the cell: the pieces must still hold on the closed cell
+            t[1] = -1.0
+            x = geom[:, 0] + t / geom[:, 1]
+            powers = np.stack([t ** k for k in range(F)], axis=-1)  # [8, N, F]
+            v = np.zeros(len(t))
+            for j in range(len(coef)):
+                term, r = np.full(len(t), coef[j]), j
+                for d in range(m.N):
+                    term = term * powers[:, d, r % F]
+                    r //= F
+                v += term
+            pts.append(x)
+            vals.append(v)
+    x, v = np.concatenate(pts), np.concatenate(vals)
+    q = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * (x + 1.0) * 0.5
+    o_out, _, o_status, scale = orc.eval(q)
+    assert (o_status == 0).all() and len(q) > 100
+    assert_values_close(v, o_out, scale)

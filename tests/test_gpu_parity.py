@@ -287,6 +287,35 @@ def test_derivative_throughput_path_equals_direct(N, level, corners):
     assert "bucket_eval" in prof and "bucket_scatter" in prof, prof
 
 
+@pytest.mark.parametrize("name", ["cub2d_testdebug", "lin3d_adapt5", "cub2d_prototest", "lin2d_adapt6"])
+def test_polynomial_evaluation_cells(golden, name):
+    """Option "ecell_poly": evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
+    (csrc/loco_cellpoly.h; coefficients formed on the device from the current values).  Same leaves and status bytes,
+    values within the 1e-12 bar of the oracle and of the term-list evaluation."""
+    pb, z = golden(name)
+    m = capi.Model.from_proto(pb, device=0)
+    assert m.info["n_poly_cells"] > 0
+    dom = m.domain.reshape(m.N, 2)
+    rng = np.random.default_rng(43)
+    q = np.concatenate([z["q"], dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.random((300_000, m.N))])
+    m.set_option("path", 4)
+    m.set_option("ecell_poly", 0)
+    a, la, sa = m.eval(q)
+    m.set_option("ecell_poly", 1)
+    b, lb, sb = m.eval(q)
+    assert np.array_equal(la, lb) and np.array_equal(sa, sb)
+    ok = sa == 0
+    assert np.isnan(b[~ok]).all()
+    assert (a[ok] != b[ok]).any(), "the polynomial cells did not run"
+    orc = oracleapi.Oracle(protoschema.read_binary(pb))
+    n = 40_000
+    o_out, o_leaf, o_status, scale = orc.eval(q[:n])
+    okn = o_status == 0
+    assert np.array_equal(lb[:n], o_leaf) and np.array_equal(sb[:n], o_status)
+    assert_values_close(b[:n][okn], o_out[okn], scale[okn])
+    assert np.abs(a[ok] - b[ok]).max() <= 1e-12 * max(1.0, scale[okn].max())
+
+
 def test_derivative_on_adaptive_tree_sorted_path(golden):
     """evalDeriv on the reference's TestDebug tree (generic leaves, cubic): sorted path keyed by evaluation cell with the
     derivative factor in the cells' term lists, against the thread-per-query kernel and the reference's own derivatives."""
