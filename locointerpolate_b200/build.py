@@ -35,10 +35,10 @@ def _nvcc() -> str:
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, HERE).encode())  # relative: the stamp must survive a copy of the tree to another path
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    h.update(" ".join(ARCH + NVCC_FLAGS).replace(HERE, ".").encode())
     return h.hexdigest()
 
 
