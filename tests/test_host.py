@@ -205,6 +205,44 @@ def test_bootstrap_generator_matches_reference_builder(N, basis, level, corners,
         assert sum(m.leaf_neighbors(l)) == fn.num_neighbors(l)
 
 
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref/liblocoref.so not built")
+@pytest.mark.parametrize("N,basis,boot,seed,n,max_level", [(2, 1, 1, 3, 14, 6), (2, 0, 1, 5, 20, 7), (3, 0, 0, 2, 10, 5), (3, 1, 0, 4, 6, 4),
+                                                         (1, 1, 1, 6, 8, 6)])
+def test_flattener_on_randomly_refined_live_grids(N, basis, boot, seed, n, max_level):
+    """Host flattener against the LIVE reference on grids refined at random leaves in random directions (the recipe of
+    TestExamples.cpp:225-240 with other seeds): leaf count, influencing-sample sets (bit-exact), neighbour counts, and the
+    evaluation-cell lists still cover every non-zero term (introspection)."""
+    grid = refapi.RefGrid(N, basis, False, 0, 0.1, boot)
+    done = grid.refine_random(seed, n, max_level)
+    assert done > 0
+    fn = grid.sampled_function()
+    m = capi.Model.from_graph(oracleapi.graph_from_ref(fn.graph()), device=capi.HOST_ONLY)
+    assert m.L == fn.L == grid.num_leaves()
+    for l in range(m.L):
+        assert np.array_equal(m.support_set(l), fn.support(l)), f"support set of leaf {l}"
+        assert sum(m.leaf_neighbors(l)) == fn.num_neighbors(l)
+    if m.info["n_eval_cells"]:
+        rng = np.random.default_rng(seed)
+        for l in range(m.L):
+            bits, first_cell, n_cells = m.eval_cells(l)
+            if n_cells == 1:
+                continue
+            centre, support, first = m.merged_terms(l)
+            box = m.leaf_box(l)
+            x = box[:, 0] + (box[:, 1] - box[:, 0]) * rng.random((400, N))
+            idx, shift = np.zeros(len(x), dtype=np.int64), 0
+            for d, b in enumerate(bits):
+                if b:
+                    g = 1 << int(b)
+                    idx |= np.clip(((x[:, d] - box[d, 0]) * g / (box[d, 1] - box[d, 0])).astype(np.int64), 0, g - 1) << shift
+                    shift += int(b)
+            nonzero = (np.abs(x[:, None, :] - centre[None]) < support[None]).all(axis=2)
+            for c in np.unique(idx):
+                listed = np.zeros(len(centre), dtype=bool)
+                listed[m.eval_cell_terms(first_cell + int(c)) - first] = True
+                assert not (nonzero[idx == c] & ~listed).any()
+
+
 def test_bootstrap_sizes_of_baseline_configs():
     """Tree sizes quoted for the BASELINE configs, built host-only with a virtual value table."""
     m = capi.Model.bootstrap(3, capi.CUBIC, 3, 1, True, device=capi.HOST_ONLY)  # C2 tree at boot 3
