@@ -241,6 +241,31 @@ def test_flattener_on_randomly_refined_live_grids(N, basis, boot, seed, n, max_l
                 listed = np.zeros(len(centre), dtype=bool)
                 listed[m.eval_cell_terms(first_cell + int(c)) - first] = True
                 assert not (nonzero[idx == c] & ~listed).any()
+    # polynomial form of the cells no knot crosses, against the reference's own evaluation at random points of the cell
+    if m.info["n_poly_cells"]:
+        F = 4 if basis == 1 else 2
+        dom = m.domain.reshape(N, 2)
+        rng = np.random.default_rng(seed + 100)
+        pts, vals = [], []
+        for cell in rng.choice(m.info["n_eval_cells"], min(300, m.info["n_eval_cells"]), replace=False):
+            pc = m.eval_cell_poly(int(cell))
+            if pc is None:
+                continue
+            geom, coef = pc
+            t = rng.uniform(-1, 1, (4, N))
+            v = np.zeros(len(t))
+            for j in range(len(coef)):
+                term, r = np.full(len(t), coef[j]), j
+                for d in range(N):
+                    term = term * t[:, d] ** (r % F)
+                    r //= F
+                v += term
+            pts.append(geom[:, 0] + t / geom[:, 1])
+            vals.append(v)
+        x, v = np.concatenate(pts), np.concatenate(vals)
+        r_out, _, r_status = fn.eval(dom[:, 0] + (dom[:, 1] - dom[:, 0]) * (x + 1.0) * 0.5)
+        assert (r_status == 0).all()
+        assert np.abs(v - r_out).max() <= 1e-12 * max(1.0, np.abs(r_out).max())
 
 
 def test_bootstrap_sizes_of_baseline_configs():
