@@ -37,3 +37,15 @@ def test_product_arm_needs_a_gpu():
     assert r.returncode != 0
     assert "no CPU path" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """launched as the driver launches the N>1 arm: rank 0 alone runs and prints, the other ranks exit 0 without work"""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c1",
+                        "--steps", "1", "--warmup", "0", "--cpu-sample", "20000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0
