@@ -219,7 +219,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[args.workload]
+        cpu_default = {"c1": 2_000_000, "c2": 200_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[args.workload]
         base, dt = cpu_reference_arm(w, args.cpu_sample or cpu_default, max(args.steps, 1), args.warmup, args.workload)
         print(json.dumps({"impl": "reference", "metric": metric, "value": base["value"], "unit": "queries/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -518,7 +518,7 @@ def measure(name, w, args, rank, world, local, config, full):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_default = {"c1": 2_000_000, "c2": 60_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[name]
+        cpu_default = {"c1": 2_000_000, "c2": 200_000, "c3": 500_000, "c4": 2048, "c4b": 512, "c5": 100_000, "a1": 600_000}[name]
         try:
             cpu, _ = cpu_reference_arm(w, args.cpu_sample or cpu_default, 1, 0, name)
         except SystemExit as e:
