@@ -154,6 +154,10 @@ int loco_eval_cell_poly(const loco_model_t *m, int64_t cell, double *geom, doubl
 /* LCAdaptiveGridCell::ranges_ of a leaf in cube coordinates: box [2N] = lo,hi per dimension (LCAdaptiveGridCell.h:89) */
 int loco_leaf_box(const loco_model_t *m, int32_t leaf, double *box);
 
+/* splitDirection_ of a leaf's parent cell (LCAdaptiveGridCell::getParent()->getSplitDirection(), what
+ * LCAdaptiveGrid::decideSplitDirection's CYCLIC policy reads, LCAdaptiveGrid.cpp:553); -1 when the root is a leaf */
+int loco_leaf_parent_split(const loco_model_t *m, int32_t leaf, int32_t *direction);
+
 /* number of leaf / border-cell neighbours of a leaf (LCAdaptiveGridCell::getNeighbors, :93-96) */
 int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, int32_t *n_border);
 
@@ -163,7 +167,12 @@ const char *loco_last_error(const loco_model_t *m);
 const char *loco_status_string(int status);
 
 /* ---- value table ----------------------------------------------------------------------------------- */
-/* replace the value table: rows [n_value_rows * value_dim], host memory */
+/* row of the value table holding LCSample::shapeInfo_ of every sample: rows [n_samples].  Samples that share one
+ * LCFunctionValue object (cubic border samples built with evalCorners=false, LCAdaptiveGrid.cpp:345-355) share a row;
+ * rows not named here hold per-cell copies that differ from the sample's value and the leaves' centerShapeInfo_. */
+int loco_sample_value_rows(const loco_model_t *m, int32_t *rows);
+/* replace the value table: rows [n_value_rows * value_dim], host memory.  The handle's host copy (what
+ * loco_model_save_proto writes) follows: tables up to 1 GiB are mirrored, larger ones are read back on demand. */
 int loco_model_set_values(loco_model_t *m, const double *values);
 /* fill the table on the device with v[row][j] = sin(0.37*j + 0.61*row + seed) + 0.001*(j % 97)
  * (synthetic mesh tables for benchmarks; never materialised on the host) */
@@ -227,7 +236,11 @@ int loco_center_error(loco_model_t *m, double threshold, double *err_max, uint8_
  * jitter points per leaf are generated ON THE DEVICE from a counter-based generator (leaf, i, seed), the
  * truth is the reference's test function family f(x) = 1 + sum_i sum_j a[i][j] * sin(3*j*x_i + p[i][j])
  * (LCRealFunction.cpp:50-63) with coefficients amp/phase [N*n_terms] supplied by the caller.
- * err_max/split: [L] device. */
+ * err_max/split: [L] device.
+ * The points are a documented function of (seed, leaf, i) so that a host can regenerate them: point p = leaf*points_per_leaf + i,
+ * dimension d:  h = splitmix64(seed ^ splitmix64(p*N + d));  r = (float)(h >> 40) / 16777215.0f;
+ * pos_d = lo_d + (double)r * (hi_d - lo_d) in cube coordinates (unfused double operations, lo/hi = loco_leaf_box).
+ * Scalar functions on tensor-product leaves run as ONE kernel without intermediates in HBM (option "fused_errgen", default 1). */
 int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, uint64_t seed, const double *amp,
                                       const double *phase, int32_t n_terms, double threshold, double *err_max,
                                       uint8_t *split, void *cuda_stream);
@@ -243,6 +256,7 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
  *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0);
  *          "ecells" 1 (default): path 4 on generic leaves sorts by evaluation cell (a regular sub-grid of the leaves with many terms,
  *                 each cell listing only the basis functions that reach it) | 0 by leaf;
+ *          "fused_errgen" 1 (default): loco_error_check_generated_device as one fused kernel where supported | 0: generate / evaluate / reduce kernels;
  *          "ecell_poly" 1: evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
  *                 (changes the summation order, within the 1e-12 bar) | 0 (default in this round): always the term list */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libloco_b200.so")
 
-SOURCES = ["loco_capi.cu", "loco_kernels.cu", "loco_tiles.cu", "loco_sorted.cu", "loco_bucket.cu", "loco_tensor.cu", "loco_mesh.cu", "loco_mesh_mma.cu", "loco_mesh_gen.cu", "loco_proto.cpp", "loco_flatten.cpp", "loco_bootstrap.cpp"]
+SOURCES = ["loco_capi.cu", "loco_kernels.cu", "loco_tiles.cu", "loco_sorted.cu", "loco_bucket.cu", "loco_tensor.cu", "loco_errgen.cu", "loco_mesh.cu", "loco_mesh_mma.cu", "loco_mesh_gen.cu", "loco_proto.cpp", "loco_flatten.cpp", "loco_bootstrap.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "--use_fast_math=false", "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
               "-Xptxas", "-v", "-I" + os.path.join(HERE, "..", "include")]

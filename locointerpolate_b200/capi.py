@@ -63,6 +63,8 @@ SIGNATURES = {
     "loco_leaf_neighbors": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "loco_last_error": (C.c_char_p, [_vp]),
     "loco_status_string": (C.c_char_p, [C.c_int]),
+    "loco_sample_value_rows": (C.c_int, [_vp, _vp]),
+    "loco_leaf_parent_split": (C.c_int, [_vp, _i32, C.POINTER(_i32)]),
     "loco_model_set_values": (C.c_int, [_vp, _vp]),
     "loco_model_fill_values_synthetic": (C.c_int, [_vp, _f64]),
     "loco_model_get_values": (C.c_int, [_vp, _i64, _i64, _vp]),
@@ -306,6 +308,17 @@ class Model:
         buf = C.create_string_buffer(1 << 16)
         self._check(lib().loco_profile_end(self._h, buf, len(buf)))
         return json.loads(buf.value.decode())
+
+    def sample_value_rows(self) -> np.ndarray:
+        """value-table row of every sample (samples sharing one value object share a row)"""
+        rows = np.empty(self.info["n_samples"], dtype=np.int32)
+        self._check(lib().loco_sample_value_rows(self._h, _ptr(rows)))
+        return rows
+
+    def leaf_parent_split(self, leaf: int) -> int:
+        d = _i32()
+        self._check(lib().loco_leaf_parent_split(self._h, leaf, C.byref(d)))
+        return d.value
 
     def set_values(self, values):
         v = _np(values, np.float64).reshape(self.info["n_value_rows"], self.D)

@@ -155,7 +155,12 @@ template <int NT, bool CUBIC, bool EXACT>
 __device__ __forceinline__ void tensor_factors(const double *blk, const Coord<NT> &x, double (&f)[NT][CUBIC ? 4 : 2], bool uniform_knots = false)
 {
 	constexpr int F = CUBIC ? 4 : 2;
-	if (CUBIC && uniform_knots) {
+	// a NaN coordinate: the reference's `d <= 1` is false, every factor of that dimension is 0 (result 0.0, status OK);
+	// the segment polynomials below would propagate the NaN instead, so such a query takes the piecewise form
+	bool finite = true;
+#pragma unroll
+	for (int d = 0; d < NT; d++) finite &= x.get(d) == x.get(d);
+	if (CUBIC && uniform_knots && finite) {
 #pragma unroll
 		for (int d = 0; d < NT; d++) {
 			const double r = blk[NT * F + d];

@@ -58,6 +58,7 @@ struct Workspace {
 struct loco_model {
 	int device = 0;
 	bool host_only = false;  // device == LOCO_HOST_ONLY: introspection only, every evaluation call fails
+	bool initial_upload = false;
 	Graph graph;
 	Flat flat;
 	DeviceModel dm{};
@@ -77,7 +78,7 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1, opt_fused_errgen = 1;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
@@ -150,6 +151,34 @@ int refresh_term_wv(loco_model *m)
 	}
 	CUDA_OK(m, cudaGetLastError());
 	CUDA_OK(m, cudaDeviceSynchronize());
+	return LOCO_OK;
+}
+
+// Host copy of the value table (Graph::values: what loco_model_save_proto serialises and loco_eval_cell_poly reads).
+// The device table is the authority once the caller replaces values; tables up to kHostValueBytes keep a host mirror,
+// larger ones (mesh tables of several GB) live on the device only and are read back on demand.
+const size_t kHostValueBytes = (size_t)1 << 30;
+
+void drop_host_values(loco_model *m)
+{
+	std::vector<double>().swap(m->graph.values);
+	m->graph.virtual_rows = m->dm.R;
+}
+
+// make Graph::values current again (after loco_model_fill_values_synthetic or a large loco_model_set_values)
+int sync_values_to_host(const loco_model *cm)
+{
+	loco_model *m = const_cast<loco_model *>(cm);
+	if (!m->graph.values.empty() || m->host_only || !m->d_values) return LOCO_OK;
+	const DeviceModel &dm = m->dm;
+	const size_t n = (size_t)dm.R * dm.D;
+	if (n * sizeof(double) > ((size_t)2 << 30))
+		return fail(m, LOCO_ERR_RANGE, "value table lives on the device and is larger than 2 GiB: too large for a protobuf message");
+	CUDA_OK(m, cudaSetDevice(m->device));
+	m->graph.values.resize(n);
+	CUDA_OK(m, cudaMemcpy2D(m->graph.values.data(), (size_t)dm.D * sizeof(double), m->d_values, (size_t)dm.value_stride * sizeof(double),
+	                        (size_t)dm.D * sizeof(double), (size_t)dm.R, cudaMemcpyDeviceToHost));
+	m->graph.virtual_rows = 0;
 	return LOCO_OK;
 }
 
@@ -329,7 +358,11 @@ int build_device_model(loco_model *m)
 		dm.root_hi_eps[i] = m->graph.tree.ranges[2 * i + 1] + kEpsilon;
 	}
 	if (!f.values.empty()) {
-		if ((rc = loco_model_set_values(m, f.values.data()))) return rc;
+		m->initial_upload = true;  // Graph::values already holds exactly these rows
+		rc = loco_model_set_values(m, f.values.data());
+		m->initial_upload = false;
+		if (rc) return rc;
+		std::vector<double>().swap(f.values);  // Graph::values is the one host copy
 	}
 	// the big term arrays are only needed on the device
 	std::vector<double>().swap(f.term_cs);
@@ -615,7 +648,8 @@ int loco_model_bootstrap(int32_t n_params, int32_t basis_type, int32_t level, in
 int loco_model_save_proto(const loco_model_t *m, const char *path, int ascii)
 {
 	if (!m || !path) return fail(m, LOCO_ERR_INVALID, "null argument");
-	if (m->graph.values.empty()) return fail(m, LOCO_ERR_INVALID, "undefined type of shape info");  // value table lives only on the device
+	if (int rc = sync_values_to_host(m)) return rc;  // values replaced on the device since construction: serialise what the kernels evaluate
+	if (m->graph.values.empty()) return fail(m, LOCO_ERR_INVALID, "undefined type of shape info");  // no value table at all (host-only handle built without values)
 	Status s = write_proto_file(m->graph, path, ascii != 0);
 	if (!s.ok) return fail(m, s.msg.rfind("could not write", 0) == 0 ? LOCO_ERR_IO : LOCO_ERR_INVALID, s.msg);
 	return LOCO_OK;
@@ -736,6 +770,7 @@ int loco_eval_cell_poly(const loco_model_t *m, int64_t cell, double *geom, doubl
 	if (!geom && !coef) return LOCO_OK;
 	if (cap < P) return fail(m, LOCO_ERR_RANGE, "coefficient buffer too small");
 	const int64_t a = f.eterm_off[(size_t)cell], b = f.eterm_off[(size_t)cell + 1];
+	if (int rc = sync_values_to_host(m)) return rc;
 	if ((int64_t)f.eterm_src.size() < b || f.mrun_term.empty() || f.term_w.empty() || m->graph.values.empty())
 		return fail(m, LOCO_ERR_INVALID, "term lists were released after upload (use a host-only handle)");
 	const double *gm = &f.epoly_geom[(size_t)f.epoly_idx[(size_t)cell] * 2 * N];
@@ -770,6 +805,33 @@ int loco_leaf_neighbors(const loco_model_t *m, int32_t leaf, int32_t *n_leaf, in
 	return LOCO_OK;
 }
 
+int loco_leaf_parent_split(const loco_model_t *m, int32_t leaf, int32_t *direction)
+{
+	if (!m || !direction) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (leaf < 0 || leaf >= m->flat.L) return fail(m, LOCO_ERR_RANGE, "leaf index out of range");
+	// tree cells are in pre-order with child1 first and leaves are numbered in that order: walk down from the root
+	const Graph::CellSet &t = m->graph.tree;
+	const int64_t C = t.size();
+	int32_t rank = 0, found = -1;
+	std::vector<int32_t> parent_dir((size_t)C, -1);
+	for (int64_t c = 0; c < C && found == -1; c++) {
+		if (t.split_dir[(size_t)c] >= 0) {
+			if (c + 1 < C) parent_dir[(size_t)c + 1] = t.split_dir[(size_t)c];
+			const int32_t c2 = t.child2[(size_t)c];
+			if (c2 >= 0 && c2 < C) parent_dir[(size_t)c2] = t.split_dir[(size_t)c];
+		} else if (rank++ == leaf) found = parent_dir[(size_t)c];
+	}
+	*direction = found;
+	return LOCO_OK;
+}
+
+int loco_sample_value_rows(const loco_model_t *m, int32_t *rows)
+{
+	if (!m || !rows) return fail(m, LOCO_ERR_INVALID, "null argument");
+	std::copy(m->graph.sample_row.begin(), m->graph.sample_row.end(), rows);
+	return LOCO_OK;
+}
+
 int loco_model_domain(const loco_model_t *m, double *ranges)
 {
 	if (!m || !ranges) return fail(m, LOCO_ERR_INVALID, "null argument");
@@ -798,6 +860,12 @@ int loco_model_set_values(loco_model_t *m, const double *values)
 	const DeviceModel &dm = m->dm;
 	CUDA_OK(m, cudaMemcpy2D(m->d_values, (size_t)dm.value_stride * sizeof(double), values, (size_t)dm.D * sizeof(double),
 	                        (size_t)dm.D * sizeof(double), (size_t)dm.R, cudaMemcpyHostToDevice));
+	// keep the host copy (what save_proto writes) in step with what the kernels evaluate
+	const size_t n = (size_t)dm.R * dm.D;
+	if (!m->initial_upload) {
+		if (n * sizeof(double) <= kHostValueBytes) { m->graph.values.assign(values, values + n); m->graph.virtual_rows = 0; }
+		else drop_host_values(m);
+	}
 	return refresh_term_wv(m);
 }
 
@@ -808,6 +876,7 @@ int loco_model_fill_values_synthetic(loco_model_t *m, double seed)
 	CUDA_OK(m, cudaSetDevice(m->device));
 	m->launches += launch_fill_values(m->d_values, m->dm.R, m->dm.D, m->dm.value_stride, seed, nullptr);
 	CUDA_OK(m, cudaGetLastError());
+	drop_host_values(m);  // the host copy is stale now; save_proto / eval_cell_poly read the table back
 	return refresh_term_wv(m);
 }
 
@@ -1062,6 +1131,12 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t ppl, uint64_t see
 	Workspace &w = m->ws[0];
 	CUDA_OK(m, cudaMemsetAsync(err_max, 0, (size_t)dm.L * 8, st));
 	CUDA_OK(m, cudaMemsetAsync(split, 0, (size_t)dm.L, st));
+	if (m->opt_fused_errgen && error_check_generated_fused_supported(dm, n_terms)) {
+		// tensor-product leaves: everything in one kernel, no intermediates in HBM (loco_errgen.cu)
+		m->launches += launch_error_check_generated_fused(dm, ppl, seed, amp, phase, n_terms, threshold, err_max, split, m->sm_count, st);
+		CUDA_OK(m, cudaGetLastError());
+		return LOCO_OK;
+	}
 	const int64_t total = (int64_t)dm.L * ppl;
 	const int64_t chunk = std::min<int64_t>(total, (int64_t)16 << 20);
 	int rc;
@@ -1091,6 +1166,7 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "uniform")) { m->opt_uniform = value; m->dm.tensor_uniform = (m->flat.tensor_uniform && value) ? 1 : 0; return LOCO_OK; }  // 0: four separate factor evaluations
 	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
+	if (!strcmp(name, "fused_errgen")) { m->opt_fused_errgen = value; return LOCO_OK; }  // 0: the three-kernel form of loco_error_check_generated_device
 	if (!strcmp(name, "ecell_poly")) {  // 1: polynomial form of the evaluation cells no knot crosses (see loco_cellpoly.h), 0: term lists
 		m->dm.epoly_idx = (value && m->dm.ecell_off) ? m->d_epoly_idx : nullptr;
 		return LOCO_OK;

@@ -138,6 +138,11 @@ int launch_jitter_points(const DeviceModel &m, int64_t points_per_leaf, uint64_t
                          const double *amp, const double *phase, int32_t n_terms, double *q_out, int32_t *leaf_out,
                          double *truth_out, cudaStream_t st);
 
+// RANDOM_SAMPLES error check in one kernel (loco_errgen.cu): generate -> evaluate in the cell -> |approx - truth| -> per-leaf max
+bool error_check_generated_fused_supported(const DeviceModel &m, int n_terms);
+int launch_error_check_generated_fused(const DeviceModel &m, int64_t ppl, uint64_t seed, const double *amp, const double *phase, int n_terms, double threshold,
+                                       double *err_max, uint8_t *split, int sm_count, cudaStream_t st);
+
 // ---- leaf-sorted tile path (loco_tiles.cu)
 struct SortWork {
 	int32_t *count;     // [L] queries per leaf

@@ -491,6 +491,9 @@ Status flatten(const Graph &g, Flat *out)
 					const double *c = &f.tl_center[((size_t)l * N + i) * F];
 					const double r = f.tl_rcp[(size_t)l * N + i], sup = f.exact_rcp ? 1.0 / r : r;
 					for (int j = 0; j + 1 < F; j++) uni = uni && (c[j + 1] - c[j] == 0.5 * sup);
+					// the four segment polynomials are evaluated at t = (x - c[1]) / h, valid on [c[1], c[2]] only:
+					// the leaf box must BE that knot interval (true for bootstrap grids, not for an arbitrary graph)
+					uni = uni && f.leaf_lo[(size_t)l * N + i] == c[1] && f.leaf_hi[(size_t)l * N + i] == c[2];
 				}
 			f.tensor_uniform = uni;
 		}

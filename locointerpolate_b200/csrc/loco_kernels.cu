@@ -230,23 +230,27 @@ __global__ void __launch_bounds__(256) error_reduce_kernel(DeviceModel m, const 
                                                             unsigned long long *__restrict__ n_bad)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= P) return;
-	if (status_in[i] != ST_OK) {
+	// no early return before the warp-wide primitives below: lanes without a point stay in the warp, flagged inactive
+	bool active = i < P;
+	if (active && status_in[i] != ST_OK) {
 		if (n_bad) atomicAdd(n_bad, 1ull);
-		return;
+		active = false;
 	}
+	const unsigned live = __ballot_sync(0xffffffffu, active);
+	if (!active) return;
 	const int32_t leaf = leaf_in[i];
 	double e = 0.0;
 	bool sp = false;
 	for (int j = 0; j < m.D; j++) {
 		double d = fabs(out[i * m.D + j] - truth[i * m.D + j]);
 		sp |= !((d - threshold) <= 0);
-		// max over components; a NaN has a larger bit pattern than any finite value, so it wins below
-		if (!(d <= e)) e = d;
+		// max over components with a STICKY NaN (a later finite component must not overwrite it): as a bit pattern a
+		// positive NaN is larger than any finite value, so it also wins the atomicMax and the all_reduce(MAX) over ranks
+		if (isnan(d) || (!isnan(e) && d > e)) e = fabs(d);
 	}
 	// warp-aggregate points of the same leaf before touching L2
 	unsigned long long bits = (unsigned long long)__double_as_longlong(e);
-	const unsigned peers = __match_any_sync(__activemask(), leaf);
+	const unsigned peers = __match_any_sync(live, leaf);
 	const int leader = __ffs(peers) - 1;
 	unsigned long long mx = bits;
 	bool any = sp;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(256) jitter_points_kernel(DeviceModel m, int64
 		uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)p * (uint64_t)m.N + (uint64_t)d));
 		float r = (float)(h >> 40) / 16777215.0f;  // 24 random bits -> float in [0,1], both ends reachable like rand()/RAND_MAX
 		double lo = m.leaf_lo[(int64_t)leaf * m.N + d], hi = m.leaf_hi[(int64_t)leaf * m.N + d];
-		double pos = lo + r * (hi - lo);
+		double pos = __dadd_rn(lo, __dmul_rn((double)r, __dsub_rn(hi, lo)));  // unfused, as the reference's C++ computes it
 		q_out[i * m.N + d] = pos;
 		if (truth_out) {
 			double alpha = (pos + 1.) / 2.;

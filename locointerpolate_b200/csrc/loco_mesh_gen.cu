@@ -291,11 +291,8 @@ int launch_mesh_generic_mma(const DeviceModel &m, const SortWork &w, const int32
 	const int64_t slice_cap = ((int64_t)28 << 20) / std::max<int64_t>(1, m.R * MG_D * 8);
 	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
 	const size_t smem = (size_t)(MG_NS * MG_K * MG_LDV + MG_NS * MG_K * MG_LDW) * sizeof(double) + 2 * MG_Q * sizeof(int32_t) + 64;
-	static const bool attr_set = [] {
-		cudaFuncSetAttribute(mesh_generic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-		return true;
-	}();
-	(void)attr_set;
+	// per launch: the attribute is per device (one process may hold models on several GPUs)
+	cudaFuncSetAttribute(mesh_generic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 	if (n_tiles < 0) tile0 = 0;
 	LOCO_KERNEL("mesh_generic_mma", st);
 	mesh_generic_mma_kernel<<<sm_count * 2, MG_THREADS, smem, st>>>(m, w.xs, sorted_row_doubles(m.N), w.offset, w.tile_off, w.tile_leaf, woff, W, out, out_stride, n_dchunks, dg,

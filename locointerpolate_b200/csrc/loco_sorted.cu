@@ -372,11 +372,9 @@ int launch_sorted_reset(const DeviceModel &m, const SortedWork &w, cudaStream_t 
 int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, const SortedWork &w,
                                     int sm_count, bool fp32, cudaStream_t st, int deriv_dir)
 {
-	static const bool scan_smem_set = [] {
-		cudaFuncSetAttribute(sorted_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kScanSeg + kScanSeg / 32) * sizeof(int)));
-		return true;
-	}();
-	(void)scan_smem_set;
+	// per launch, not once per process: the attribute belongs to the current device's context and one process may hold
+	// models on several GPUs
+	cudaFuncSetAttribute(sorted_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kScanSeg + kScanSeg / 32) * sizeof(int)));
 	if (Q <= 0) return 0;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_SCASE(NT)                                                                                       \

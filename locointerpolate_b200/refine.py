@@ -29,14 +29,18 @@ def leaf_geometry(model: Model) -> Tuple[np.ndarray, np.ndarray]:
     return width.prod(axis=1), level
 
 
-def cyclic_direction(model: Model, leaf: int) -> int:
-    """direction after the parent's in cyclic order (LCAdaptiveGrid.cpp:553 generalised from 2 to N parameters).  On the
-    trees the reference builds (bootstrapUniformSplit cycles 0..N-1) that is the first dimension of largest extent."""
+def cyclic_direction(model: Model, leaf: int, literal: bool = False) -> int:
+    """CYCLIC split policy.  Default: the direction after the parent's in cyclic order, LCAdaptiveGrid.cpp:553 generalised
+    from 2 to N parameters -- on the trees the reference builds (bootstrapUniformSplit cycles 0..N-1) that is the first
+    dimension of largest extent.  literal=True: the reference's expression as written, `(parentDir + 1) % 2`, which for
+    N > 2 only ever alternates between directions 0 and 1 (SURVEY.md 8a hazard H7); identical to the default for N = 2."""
+    if literal:
+        return (model.leaf_parent_split(leaf) + 1) % 2
     box = model.leaf_box(leaf)
     return int(np.argmax(box[:, 1] - box[:, 0]))
 
 
-def select_splits(model: Model, threshold: float, max_level: int):
+def select_splits(model: Model, threshold: float, max_level: int, literal_cyclic: bool = False):
     """One batched decideSplit over all leaves.  Returns (leaves, directions, err): the flagged leaves of the LARGEST
     flagged size class (what the reference's heap would pop next), in descending leaf order so that splitting one of them
     leaves the indices of those still to come untouched (leaves are numbered depth-first, child1 first)."""
@@ -47,18 +51,18 @@ def select_splits(model: Model, threshold: float, max_level: int):
         return [], [], err
     top = volume[flagged].max()
     chosen = [int(l) for l in flagged[volume[flagged] >= top * (1 - 1e-12)]][::-1]
-    return chosen, [cyclic_direction(model, l) for l in chosen], err
+    return chosen, [cyclic_direction(model, l, literal_cyclic) for l in chosen], err
 
 
 def adaptive_sample_passes(get_model: Callable[[], Model], surgery: Callable[[int, int], None], threshold: float, max_level: int,
-                           max_passes: int = 256) -> List[dict]:
+                           max_passes: int = 256, literal_cyclic: bool = False) -> List[dict]:
     """Level-synchronous adaptiveSample: repeat {flatten -> batched error check on the device -> host surgery on the
     flagged leaves of the largest size class} until no leaf is flagged.  `get_model()` returns the model of the grid's
     current state (from_graph of whatever the host's grid serialises to); `surgery(leaf, direction)` is refineCell."""
     log = []
     for _ in range(max_passes):
         model = get_model()
-        leaves, dirs, err = select_splits(model, threshold, max_level)
+        leaves, dirs, err = select_splits(model, threshold, max_level, literal_cyclic)
         log.append({"leaves": model.L, "flagged": len(leaves), "max_center_error": float(np.nanmax(err)) if len(err) else 0.0})
         if not leaves:
             return log

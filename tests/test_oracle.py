@@ -138,3 +138,44 @@ def test_cubic_derivative_of_linear_function(golden, name):
     for d in range(orc.N):
         out, _, status, _ = orc.eval_deriv(z["q"], d)
         assert np.abs(out[inside & (status == 0)] - (d + 1) / 2).max() < 1e-11
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref/liblocoref.so not built")
+@pytest.mark.parametrize("N,basis,level,corners", [(6, 1, 1, False), (4, 0, 3, True)])
+def test_mesh_restatement_at_baseline_shapes(N, basis, level, corners):
+    """The mesh oracle of the GPU parity tests (tests/test_gpu_baseline_shapes.py) at the BASELINE trees: 6-D cubic with
+    evalCorners=false (4,096 influencing samples per leaf, border samples sharing value rows) and 4-D linear bootstrap 3.
+    CPU restatement with D components == the reference's own (sample, weight) lists applied to the value rows."""
+    import tempfile
+    import os
+    import protoschema
+    from locointerpolate_b200 import capi
+    twin = capi.Model.bootstrap(N, basis, level, 1, corners, fn=lambda p: float(np.sin(3 * p).sum()), device=capi.HOST_ONLY)
+    tmp = tempfile.mktemp(suffix=".pb")
+    twin.save_proto(tmp)
+    g = protoschema.read_binary(tmp)
+    os.unlink(tmp)
+    fn = refapi.RefFn.from_graph(g)
+    rows = twin.sample_value_rows()
+    assert len(rows) == fn.S
+    D = 5
+    rng = np.random.default_rng(4)
+    table = rng.standard_normal((int(rows.max()) + 1, D))
+    per_sample = table[rows]   # samples sharing a value object carry equal rows
+    g.D = D
+    g.sample_value = per_sample
+    g.sample_value_group = None
+    g.cell_sample_value = g.border_sample_value = g.cell_center_value = g.border_center_value = None
+    orc = oracleapi.Oracle(g.normalise())
+    q = rng.random((40, N)) * 1.0000004 - 0.0000002
+    q[:8] = np.round(q[:8] * 4) / 4
+    out, leaf, status, scale = orc.eval(q)
+    r_out, r_leaf, r_status = fn.eval(q)
+    assert np.array_equal(leaf, r_leaf) and np.array_equal(status, r_status) and (status == 0).all()
+    for i in range(len(q)):
+        ids, w = fn.weights(int(leaf[i]), q[i] * 2 - 1)
+        ref = np.zeros(D)
+        for k in range(len(ids)):
+            ref += w[k] * per_sample[ids[k]]
+        assert np.abs(out[i] - ref).max() <= 1e-12 * max(scale[i], 1e-300)
+        assert abs(w.sum() - 1) < 1e-12
