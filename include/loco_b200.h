@@ -179,6 +179,8 @@ int loco_model_set_values(loco_model_t *m, const double *values);
 int loco_model_fill_values_synthetic(loco_model_t *m, double seed);
 /* copy rows [row0, row0+n) to host */
 int loco_model_get_values(const loco_model_t *m, int64_t row0, int64_t n, double *out);
+/* copy components [col0, col0+n) of EVERY row to host: out [n_value_rows * n] (spot checks of tables too large to read back) */
+int loco_model_get_value_columns(const loco_model_t *m, int64_t col0, int64_t n, double *out);
 
 /* ---- the hot path ------------------------------------------------------------------------------------
  * LCSampledFunction::evalShapeInfo(params, &result) (LCSampledFunction.cpp:69-78) for a batch:
@@ -203,6 +205,11 @@ int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t n_queries, 
  * synchronises the stream once (to split the sorted batch into runs). */
 int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t n_queries, double *ring, int64_t ring_queries,
                                 double *checksum, int32_t *leaf, uint8_t *status, void *cuda_stream);
+
+/* the same from HOST buffers (q in, checksum / leaf / status out; copies inside the call): the ring is an internal device
+ * scratch of ring_queries results (0 = a default sized for ~16 GiB, at least one 64-query tile per leaf run) */
+int loco_eval_batch_ring(loco_model_t *m, const double *q, int64_t n_queries, int64_t ring_queries, double *checksum, int32_t *leaf,
+                         uint8_t *status);
 
 /* ---- derivative ------------------------------------------------------------------------------------------
  * LCSampledFunction::evalDeriv(params, direction, &result) (LCSampledFunction.cpp:61-67) for a batch:
@@ -245,6 +252,21 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
                                       const double *phase, int32_t n_terms, double threshold, double *err_max,
                                       uint8_t *split, void *cuda_stream);
 
+/* ---- multi-GPU result exchange ---------------------------------------------------------------------------
+ * One process per GPU, the model replicated, the query batch sharded.  The per-shard results travel to the
+ * consuming GPU over NVLink through the COPY ENGINES, not through SM kernels: the consumer exports a device buffer, every
+ * producer maps it (CUDA IPC) and pushes its shard with an asynchronous peer copy on a side stream while its SMs evaluate the
+ * next batch.  (locointerpolate_b200/shard.py: RotatingExchange drives these; NCCL stays for the completion signal and the
+ * error-maxima all-reduce.)  No model handle: errors are reported through loco_last_error(NULL).
+ *   create : cudaMalloc on `device` + export; handle = 64 opaque bytes to send to the peers
+ *   open   : map a peer's buffer into this process (peer access is enabled lazily by the runtime); *dptr is valid on `device`
+ *   copy   : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `cuda_stream` -- device-to-device, either side may be a mapped peer buffer */
+int loco_peer_buffer_create(int device, size_t bytes, void **dptr, unsigned char handle[64]);
+int loco_peer_buffer_open(int device, const unsigned char handle[64], void **dptr);
+int loco_peer_buffer_close(int device, void *dptr);
+int loco_peer_buffer_free(int device, void *dptr);
+int loco_peer_copy_async(void *dst, const void *src, size_t bytes, void *cuda_stream);
+
 /* ---- tuning / accounting -------------------------------------------------------------------------------- */
 /* options: "lut" 1 locate grid before the k-d descent (default) | 0 descent from the root only;
  *          "path" 0 auto | 1 direct (thread per query) | 2 leaf-sorted TMA tiles | 3 direct without the tensor-leaf shortcut |
@@ -256,6 +278,12 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t points_per_leaf, 
  *          "mesh_simt" 1: mesh-valued tiles with DFMA register tiles instead of the fp64 MMA pipe (default 0);
  *          "ecells" 1 (default): path 4 on generic leaves sorts by evaluation cell (a regular sub-grid of the leaves with many terms,
  *                 each cell listing only the basis functions that reach it) | 0 by leaf;
+ *          "leaf_poly" 1 (default): scalar functions on tensor-product leaves that lie inside one polynomial piece of every basis function
+ *                 (every bootstrap grid) evaluate the leaf's single tensor-product polynomial by nested Horner (changes the
+ *                 summation order, within the 1e-12 bar) | 0: N*F basis polynomials + sum-factorised contraction;
+ *          "adaptive" 1 (default): with "path" 0 big scalar batches on tensor-product leaves take the leaf buckets (path 5) while the batches
+ *                 seen so far fit the buckets' uniform-batch capacity, and the exact counting sort (path 4) once more than 4 % of the queries
+ *                 overflow (skewed batches); decided from counters the kernels keep, without synchronisation | 0: always the buckets;
  *          "fused_errgen" 1 (default): loco_error_check_generated_device as one fused kernel where supported | 0: generate / evaluate / reduce kernels;
  *          "ecell_poly" 1: evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
  *                 (changes the summation order, within the 1e-12 bar) | 0 (default in this round): always the term list */

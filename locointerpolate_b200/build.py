@@ -42,11 +42,17 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
+def source_digest() -> str:
+    """sha256 over every source and header of the library and the compiler flags: identifies the kernels a measurement
+    (an ncu capture in profiles/traffic.json) was taken from"""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "loco_b200.h")]
+    return _digest(deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "loco_b200.h")]
     stamp = os.path.join(OBJ, "stamp")
-    dig = _digest(deps)
+    dig = source_digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     os.makedirs(OBJ, exist_ok=True)

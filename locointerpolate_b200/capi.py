@@ -71,6 +71,8 @@ SIGNATURES = {
     "loco_eval_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "loco_eval_batch_device": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "loco_eval_batch_ring_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "loco_eval_batch_ring": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "loco_model_get_value_columns": (C.c_int, [_vp, _i64, _i64, _vp]),
     "loco_model_domain": (C.c_int, [_vp, _vp]),
     "loco_leaf_box": (C.c_int, [_vp, _i32, _vp]),
     "loco_merged_terms": (C.c_int, [_vp, _i32, _vp, _vp, _i32, C.POINTER(_i32), C.POINTER(_i64)]),
@@ -83,6 +85,11 @@ SIGNATURES = {
     "loco_error_check_device": (C.c_int, [_vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp]),
     "loco_center_error": (C.c_int, [_vp, _f64, _vp, _vp]),
     "loco_error_check_generated_device": (C.c_int, [_vp, _i64, C.c_uint64, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "loco_peer_buffer_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "loco_peer_buffer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    "loco_peer_buffer_close": (C.c_int, [C.c_int, _vp]),
+    "loco_peer_buffer_free": (C.c_int, [C.c_int, _vp]),
+    "loco_peer_copy_async": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "loco_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "loco_kernel_launches": (_i64, [_vp]),
     "loco_profile_begin": (C.c_int, [_vp]),
@@ -216,6 +223,37 @@ def child2_from_preorder(split_dir) -> np.ndarray:
             child2[i] = c2
             size[i] = 1 + size[c1] + size[c2]
     return child2
+
+
+def _check0(rc):
+    if rc != 0:
+        raise LocoError(rc, lib().loco_last_error(None).decode())
+
+
+def peer_buffer_create(device: int, nbytes: int):
+    """(device pointer, 64-byte handle) of a fresh device buffer other processes of the box can map"""
+    p = _vp()
+    h = C.create_string_buffer(64)
+    _check0(lib().loco_peer_buffer_create(device, nbytes, C.byref(p), h))
+    return p.value, h.raw
+
+
+def peer_buffer_open(device: int, handle: bytes) -> int:
+    p = _vp()
+    _check0(lib().loco_peer_buffer_open(device, C.create_string_buffer(handle, 64), C.byref(p)))
+    return p.value
+
+
+def peer_buffer_close(device: int, ptr: int):
+    _check0(lib().loco_peer_buffer_close(device, ptr))
+
+
+def peer_buffer_free(device: int, ptr: int):
+    _check0(lib().loco_peer_buffer_free(device, ptr))
+
+
+def peer_copy_async(dst: int, src: int, nbytes: int, stream: int = 0):
+    _check0(lib().loco_peer_copy_async(dst, src, nbytes, stream or None))
 
 
 class Model:
@@ -354,6 +392,15 @@ class Model:
                          status_ptr: int = 0, stream: int = 0):
         self._check(lib().loco_eval_batch_ring_device(self._h, q_ptr, Q, ring_ptr, ring_queries, checksum_ptr, leaf_ptr or None,
                                                       status_ptr or None, stream or None))
+
+    def eval_ring_raw(self, q_ptr: int, Q: int, ring_queries: int, checksum_ptr: int, leaf_ptr: int = 0, status_ptr: int = 0):
+        """host pointers: queries in, per-query checksums (+ leaf, status) out; the ring lives inside the handle"""
+        self._check(lib().loco_eval_batch_ring(self._h, q_ptr, Q, ring_queries, checksum_ptr, leaf_ptr or None, status_ptr or None))
+
+    def get_value_columns(self, col0: int, n: int) -> np.ndarray:
+        out = np.empty((self.info["n_value_rows"], n))
+        self._check(lib().loco_model_get_value_columns(self._h, col0, n, _ptr(out)))
+        return out
 
     # ---- derivative along one cube direction (scalar functions)
     def eval_deriv(self, q, direction: int):

@@ -64,8 +64,20 @@ __device__ __forceinline__ uint32_t lut_lookup(const DeviceModel &m, const Coord
 			const int bits = m.lut_bits[d];
 			if (bits == 0) continue;
 			const int last = (1 << bits) - 1;
-			const double *B = m.lut_bounds + m.lut_boff[d];
 			const double xv = x.get(d);
+			if ((m.lut_uniform_mask >> d) & 1u) {
+				// boundaries are exactly lo + i*h, h and 1/h powers of two: (x - lo) rounds monotonically and the multiplication is
+				// exact, so floor() can only be off by one DOWNWARDS-missing, when the rounded difference landed ON boundary i
+				// while x itself lies below it -- one exact fma gives that boundary
+				int i = (int)fmin(fmax((xv - m.lut_lo[d]) * m.lut_inv[d], 0.0), (double)last);
+				const double b0 = fma((double)i, m.lut_h[d], m.lut_lo[d]);
+				if (i > 0 && xv < b0) i--;
+				ok &= xv == xv;  // a NaN coordinate takes the descent from the root (child2 at every split)
+				idx |= (uint32_t)i << shift;
+				shift += bits;
+				continue;
+			}
+			const double *B = m.lut_bounds + m.lut_boff[d];
 			int i = (int)fmin(fmax((xv - m.lut_lo[d]) * m.lut_inv[d], 0.0), (double)last);
 			double b0 = __ldg(B + i), b1 = __ldg(B + i + 1);
 			if (i > 0 && xv < b0) { i--; b1 = b0; b0 = __ldg(B + i); }              // rare: the estimate rounded across a boundary
@@ -260,6 +272,92 @@ __device__ __forceinline__ double tensor_eval_scalar(const DeviceModel &m, const
 	double f[NT][F];
 	tensor_factors<NT, CUBIC, EXACT>(blk, x, f, m.tensor_uniform != 0);
 	return TensorContract<NT, F, NT - 1>::run(blk + m.tl_voff, f, m.tensor_K / F);
+}
+
+// ---- per-leaf polynomial form -------------------------------------------------------------------------
+// sum_j coef[j] prod_d t[d]^(j_d) by nested Horner (dimension 0 innermost): F^N - 1 fused multiply-adds and no basis
+// evaluation at all, against N*F basis polynomials + (F^N + F^(N-1) + ...) FMAs of the factor/contraction form.
+template <int NT, int F, int LEVEL>
+struct TensorHorner {
+	static __device__ __forceinline__ double run(const double *v, const double (&t)[NT], int stride)
+	{
+		if (ipow_c(F, LEVEL + 1) > 64) {
+			double tl = t[0];
+#pragma unroll
+			for (int i = 1; i < NT; i++) tl = (i == LEVEL) ? t[i] : tl;
+			double s = TensorHorner<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + (F - 1) * stride, t, stride / F);
+#pragma unroll 1
+			for (int j = F - 2; j >= 0; j--) s = fma(s, tl, TensorHorner<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, t, stride / F));
+			return s;
+		} else {
+			double s = TensorHorner<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + (F - 1) * stride, t, stride / F);
+#pragma unroll
+			for (int j = F - 2; j >= 0; j--) s = fma(s, t[LEVEL], TensorHorner<NT, F, (LEVEL > 0 ? LEVEL - 1 : 0)>::run(v + j * stride, t, stride / F));
+			return s;
+		}
+	}
+};
+template <int NT, int F>
+struct TensorHorner<NT, F, 0> {
+	static __device__ __forceinline__ double run(const double *v, const double (&t)[NT], int)
+	{
+		double c[F];
+#pragma unroll
+		for (int j = 0; j < F; j += 2) {
+			const double2 p = *reinterpret_cast<const double2 *>(v + j);
+			c[j] = p.x; c[j + 1] = p.y;
+		}
+		double s = c[F - 1];
+#pragma unroll
+		for (int j = F - 2; j >= 0; j--) s = fma(s, t[0], c[j]);
+		return s;
+	}
+};
+// level 1: one F x F slab, all of it requested first (independent 128-bit loads in flight together), as in TensorContract
+template <int NT, int F>
+struct TensorHorner<NT, F, 1> {
+	static __device__ __forceinline__ double run(const double *v, const double (&t)[NT], int)
+	{
+		double2 c[F * F / 2];
+#pragma unroll
+		for (int i = 0; i < F * F / 2; i++) c[i] = reinterpret_cast<const double2 *>(v)[i];
+		double row[F];
+#pragma unroll
+		for (int j = 0; j < F; j++) {
+			double s = c[j * (F / 2) + F / 2 - 1].y;
+#pragma unroll
+			for (int i = F - 2; i >= 0; i--) s = fma(s, t[0], (i & 1) ? c[j * (F / 2) + i / 2].y : c[j * (F / 2) + i / 2].x);
+			row[j] = s;
+		}
+		double s = row[F - 1];
+#pragma unroll
+		for (int j = F - 2; j >= 0; j--) s = fma(s, t[1], row[j]);
+		return s;
+	}
+};
+
+// Value of a scalar function on a tensor-product leaf.  pblk != nullptr: the leaf's polynomial block (shared or global
+// memory).  A query outside the leaf box (only possible in the +-1e-6 acceptance band around the ROOT box, where the basis
+// functions switch pieces -- the linear hat is only C0 there) or with a NaN coordinate takes the factor form on the leaf's
+// classic block, i.e. exactly the piecewise definition of LC{Linear,Cubic}BSpline::eval; blk == nullptr: read from global memory.
+template <int NT, bool CUBIC, bool EXACT>
+__device__ __forceinline__ double tensor_leaf_value(const DeviceModel &m, const double *blk, const double *pblk, int32_t leaf, const Coord<NT> &x)
+{
+	constexpr int F = CUBIC ? 4 : 2;
+	if (pblk) {
+		double t[NT];
+		bool inside = true;
+#pragma unroll
+		for (int d = 0; d < NT; d++) {
+			const double2 g = *reinterpret_cast<const double2 *>(pblk + 2 * d);
+			t[d] = (x.get(d) - g.x) * g.y;
+			inside &= fabs(t[d]) <= 1.0;
+		}
+		if (inside) return TensorHorner<NT, F, NT - 1>::run(pblk + 2 * NT, t, m.tensor_K / F);
+		blk = nullptr;  // (a staged classic block is not available next to a staged polynomial block)
+	}
+	if (!blk) blk = m.tl_block + (int64_t)leaf * m.tl_stride;
+	return tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
 }
 
 // One dimension of LCLinearBSpline::eval (LCBasisFunction.cpp:283-288): d = |x-c|/s; d <= 1 ? 1-d : 0.

@@ -95,7 +95,13 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 #pragma unroll
 			for (int d = 0; d < RS; d += 4) st_sector_cg(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
 		} else {
-			ovf[atomicAdd(n_ovf, 1)] = (int32_t)i;
+			// one atomic per warp on the list counter (a skewed batch sends most of a warp here)
+			const unsigned peers = __activemask();
+			const int leader = __ffs(peers) - 1, lane_id = threadIdx.x & 31;
+			int base = 0;
+			if (lane_id == leader) base = atomicAdd(n_ovf, __popc(peers));
+			base = __shfl_sync(peers, base, leader);
+			ovf[base + __popc(peers & ((1u << lane_id) - 1))] = (int32_t)i;
 		}
 	}
 }
@@ -116,18 +122,24 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int NT, bool CUBIC, bool EXACT, bool FP32, bool DBL, bool DERIV>
 __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out,
                                                               const double *__restrict__ q, const int32_t *__restrict__ leaf_in, const int32_t *__restrict__ ovf,
-                                                              const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next, int dir)
+                                                              const int32_t *__restrict__ n_ovf, int32_t *n_ovf_next, int dir, SkewStats *stats, int64_t n_chunk)
 {
-	if (blockIdx.x == 0 && threadIdx.x == 0) *n_ovf_next = 0;  // the counter of the NEXT chunk on this workspace (nobody reads it now)
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		*n_ovf_next = 0;  // the counter of the NEXT chunk on this workspace (nobody reads it now)
+		if (stats) { stats->overflow += *n_ovf; stats->total += n_chunk; }  // one writer per workspace slot (its chunks are serialised on one stream)
+	}
 	constexpr int RS = brec_doubles(NT);
 	extern __shared__ __align__(16) double s_blk[];  // [8][DBL ? 2 : 1][tl_stride]  (+ K/2 doubles per slot holding the fp32 values in fp32 mode)
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n_warps = gridDim.x * 8;
-	const int slot_doubles = ((FP32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
+	// the leaf's polynomial block where the model has one (values only; derivatives and the fp32 mode use the classic block)
+	const bool poly = !FP32 && !DERIV && m.tl_poly != nullptr;
+	const int slot_doubles = ((FP32 ? m.tl_voff + (m.tensor_K + 1) / 2 : (poly ? m.tp_stride : m.tl_stride)) + 1) & ~1;
 	double *slot0 = s_blk + (size_t)warp * (DBL ? 2 : 1) * slot_doubles;
 	auto issue_block = [&](int32_t lf, double *dst) {
-		const char *src = reinterpret_cast<const char *>(m.tl_block + (int64_t)lf * m.tl_stride);
-		const int n16 = (FP32 ? m.tl_voff : m.tl_stride) / 2;
+		const char *src = poly ? reinterpret_cast<const char *>(m.tl_poly + (int64_t)lf * m.tp_stride)
+		                       : reinterpret_cast<const char *>(m.tl_block + (int64_t)lf * m.tl_stride);
+		const int n16 = (FP32 ? m.tl_voff : (poly ? m.tp_stride : m.tl_stride)) / 2;
 		for (int e = lane; e < n16; e += 32) cp_async16(dst + 2 * e, src + 16 * e);
 		if (FP32) {
 			const char *vs = reinterpret_cast<const char *>(m.tl_vals_f32 + (int64_t)lf * m.tensor_K);
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 				double r;
 				if constexpr (DERIV) r = tensor_eval_scalar_deriv<NT, EXACT>(m, blk, x, dir);
 				else if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
-				else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
+				else r = poly ? tensor_leaf_value<NT, CUBIC, EXACT>(m, nullptr, blk, leaf, x) : tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
 				out[qi] = r;
 			}
 		}
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 		map_to_cube<NT>(m, p, x);
 		const double *gblk = m.tl_block + (int64_t)leaf_in[i] * m.tl_stride;
 		if constexpr (DERIV) out[i] = tensor_eval_scalar_deriv<NT, EXACT>(m, gblk, x, dir);
-		else out[i] = tensor_eval_scalar<NT, CUBIC, EXACT>(m, gblk, x);
+		else out[i] = tensor_leaf_value<NT, CUBIC, EXACT>(m, gblk, poly ? m.tl_poly + (int64_t)leaf_in[i] * m.tp_stride : nullptr, leaf_in[i], x);
 	}
 }
 
@@ -211,13 +223,14 @@ void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, in
 	{
 		LOCO_KERNEL("bucket_eval", st);
 		const bool f32 = fp32 && m.tl_vals_f32 && (m.tensor_K % 4) == 0 && deriv_dir < 0;
-		const int slot_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : m.tl_stride) + 1) & ~1;
+		const bool poly = !f32 && deriv_dir < 0 && m.tl_poly != nullptr;
+		const int slot_doubles = ((f32 ? m.tl_voff + (m.tensor_K + 1) / 2 : (poly ? m.tp_stride : m.tl_stride)) + 1) & ~1;
 		const bool dbl = (size_t)16 * slot_doubles * sizeof(double) <= 72 * 1024;  // two slots per warp while 3 CTAs per SM still fit
 		const size_t smem = (size_t)8 * (dbl ? 2 : 1) * slot_doubles * sizeof(double);
 		const int grid = std::min(sm_count * 3, (m.L + 7) / 8);
 		auto launch = [&](auto kern) {
 			if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next, deriv_dir);
+			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next, deriv_dir, w.stats, Q);
 		};
 		if constexpr (CUBIC) {
 			if (deriv_dir >= 0) {
@@ -249,6 +262,7 @@ size_t bucket_work_bytes(const DeviceModel &m, int64_t chunk)
 BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base)
 {
 	BucketWork w;
+	w.stats = nullptr;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
 	w.count = p; p += m.L;
 	w.n_ovf = p; p += 4;

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -48,6 +49,8 @@ struct Workspace {
 	cudaStream_t stream = nullptr;
 	void *q = nullptr, *out = nullptr, *leaf = nullptr, *status = nullptr, *W = nullptr, *truth = nullptr, *misc = nullptr, *sorted = nullptr;
 	void *sortedx[3] = {nullptr, nullptr, nullptr};
+	void *h_q = nullptr, *h_out = nullptr, *h_leaf = nullptr, *h_status = nullptr;  // page-locked staging of the host-buffer path (pageable callers)
+	size_t h_q_b = 0, h_out_b = 0, h_leaf_b = 0, h_status_b = 0;
 	void *woff = nullptr;  // weight-block offsets of the generic mesh path
 	size_t woff_b = 0;  // workspaces of the additional streams of the sorted path
 	size_t q_b = 0, out_b = 0, leaf_b = 0, status_b = 0, W_b = 0, truth_b = 0, misc_b = 0, sorted_b = 0, sortedx_b[3] = {0, 0, 0};
@@ -72,19 +75,24 @@ struct loco_model {
 	double *d_epoly = nullptr;
 	int32_t n_epoly = 0;
 	double *d_tl_block = nullptr;
+	double *d_tl_poly = nullptr;  // per-leaf polynomial blocks (option "leaf_poly")
 	float *d_tl_vals_f32 = nullptr;
 	int64_t n_terms = 0;
 	int sm_count = 148;
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1, opt_fused_errgen = 1;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1, opt_fused_errgen = 1, opt_leaf_poly = 1, opt_adaptive = 1;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
 	// kernels of one chunk overlap the evaluation of another
 	cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+	// skew statistics (host-mapped, one entry per internal stream): see SkewStats in loco_device.h
+	SkewStats *h_stats = nullptr, *d_stats = nullptr;
+	long long seen_overflow = 0, seen_total = 0;
+	bool skewed = false;  // the recent batches overflowed their leaf buckets: scalar batches take the exact counting sort
 };
 
 namespace {
@@ -148,6 +156,7 @@ int refresh_term_wv(loco_model *m)
 		m->launches += launch_update_eterm_wv(m->dm, m->d_eterm_wv, nullptr);
 		m->launches += launch_update_epoly(m->dm, m->d_epoly_cell, m->n_epoly, m->d_epoly, nullptr);
 		m->launches += launch_update_tensor_vals(m->dm, m->d_tl_block, m->d_tl_vals_f32, nullptr);
+		m->launches += launch_update_tensor_poly(m->dm, m->d_tl_poly, m->dm.tp_stride, nullptr);  // from the refreshed leaf values
 	}
 	CUDA_OK(m, cudaGetLastError());
 	CUDA_OK(m, cudaDeviceSynchronize());
@@ -323,6 +332,17 @@ int build_device_model(loco_model *m)
 			m->d_tl_vals_f32 = const_cast<float *>(dv);
 			dm.tl_vals_f32 = dv;
 		}
+		// per-leaf polynomial form for scalar functions: leaves inside one polynomial piece of every basis function;
+		// K <= 256 keeps the monomial form well inside the 1e-12 bar (cubic N <= 4, linear N <= 8)
+		dm.tl_poly = nullptr; dm.tp_stride = 0;
+		if (f.D == 1 && f.tensor_poly && K <= 256) {
+			dm.tp_stride = (2 * N + K + 1) & ~1;
+			std::vector<double> zeros((size_t)f.L * dm.tp_stride, 0.0);
+			const double *dp = nullptr;
+			if ((rc = upload(m, zeros, &dp))) return rc;
+			m->d_tl_poly = const_cast<double *>(dp);
+			if (m->opt_leaf_poly) dm.tl_poly = dp;
+		}
 		std::vector<int32_t> fold_off = narrow(m, f.fold_off, &ok);
 		if ((rc = upload(m, fold_off, &dm.fold_off))) return rc;
 		if ((rc = upload(m, f.fold_row, &dm.fold_row))) return rc;
@@ -340,6 +360,7 @@ int build_device_model(loco_model *m)
 		if (pow2) dm.dom_exact_mask |= 1u << d;
 	}
 	dm.lut = nullptr;
+	dm.lut_uniform_mask = 0;
 	if (!f.lut.empty() && m->opt_lut) {
 		if ((rc = upload(m, f.lut, &dm.lut))) return rc;
 		if ((rc = upload(m, f.lut_bounds, &dm.lut_bounds))) return rc;
@@ -349,6 +370,14 @@ int build_device_model(loco_model *m)
 			const double lo = f.lut_bounds[(size_t)f.lut_boff[d]], hi = f.lut_bounds[(size_t)f.lut_boff[d] + ((size_t)1 << f.lut_bits[d])];
 			dm.lut_lo[d] = lo;
 			dm.lut_inv[d] = (double)((int64_t)1 << f.lut_bits[d]) / (hi - lo);
+			// uniform dyadic boundaries?  h and 1/h exact powers of two and every stored boundary == fma(i, h, lo) bit for bit
+			const double h = (hi - lo) / (double)((int64_t)1 << f.lut_bits[d]);
+			int e2;
+			bool uni = f.lut_bits[d] > 0 && h > 0 && std::frexp(h, &e2) == 0.5 && std::isnormal(h) && std::isnormal(1.0 / h) && dm.lut_inv[d] == 1.0 / h;
+			for (int64_t i = 0; uni && i <= ((int64_t)1 << f.lut_bits[d]); i++)
+				uni = f.lut_bounds[(size_t)f.lut_boff[d] + (size_t)i] == std::fma((double)i, h, lo);
+			dm.lut_h[d] = h;
+			if (uni) dm.lut_uniform_mask |= 1u << d;
 		}
 	}
 	dm.path_consistent = f.path_consistent ? 1 : 0;
@@ -378,6 +407,9 @@ int build_device_model(loco_model *m)
 		CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_join[k], cudaEventDisableTiming));
 	}
 	CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+	CUDA_OK(m, cudaHostAlloc((void **)&m->h_stats, 4 * sizeof(SkewStats), cudaHostAllocMapped));
+	memset(m->h_stats, 0, 4 * sizeof(SkewStats));
+	CUDA_OK(m, cudaHostGetDevicePointer((void **)&m->d_stats, m->h_stats, 0));
 	return LOCO_OK;
 }
 
@@ -406,8 +438,25 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool big = Q >= (int64_t)dm.L * 24 && Q >= (1 << 16) && leaf_bytes > 96 * 1024;
 		const bool sorted = !in_cube && (m->opt_path == 4 || (m->opt_path == 0 && big));
 		const bool tiles = !in_cube && m->opt_path == 2;
-		const bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256)) &&
-		                    (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE);
+		bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256)) &&
+		              (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE);
+		if (bucket && m->opt_path == 0 && m->opt_adaptive && m->h_stats) {
+			// Automatic dispatch between the single-pass leaf buckets (capacity sized for a uniform batch) and the exact counting
+			// sort: the kernels of both paths add {queries beyond a bucket's capacity, queries seen} to host-mapped counters, and
+			// the counters of the batches evaluated SO FAR decide this call (no synchronisation: a stale value only delays the
+			// switch by a call).  Skewed batches -- optimisation trajectories, lattice sweeps in a few leaves -- would overflow
+			// their buckets into the thread-per-query fallback; the counting sort has no capacity and evaluates them in leaf order.
+			long long ovf = 0, tot = 0;
+			for (int k = 0; k < 4; k++) { ovf += ((volatile SkewStats *)m->h_stats)[k].overflow; tot += ((volatile SkewStats *)m->h_stats)[k].total; }
+			const long long d_ovf = ovf - m->seen_overflow, d_tot = tot - m->seen_total;
+			if (d_tot >= (1 << 20)) {
+				const double frac = (double)d_ovf / (double)d_tot;
+				if (!m->skewed && frac > 0.04) m->skewed = true;
+				else if (m->skewed && frac < 0.01) m->skewed = false;
+				m->seen_overflow = ovf; m->seen_total = tot;
+			}
+			if (m->skewed) bucket = false;  // `sorted` is set for every batch that qualifies for the buckets
+		}
 		// derivatives on generic leaves with the cubic basis: the sorted path with the derivative factor in its term lists
 		const bool sorted_deriv = deriv_dir >= 0 && !bucket && sorted && dm.basis == CUBIC_BSPLINE && dm.tensor_F == 0;
 		if (deriv_dir >= 0 && !bucket && !sorted_deriv) {
@@ -432,6 +481,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 				size_t *have = k == 0 ? &w.sorted_b : &w.sortedx_b[k - 1];
 				if ((rc = grow(m, buf, have, bucket_work_bytes(dm, chunk)))) return rc;
 				bw[k] = carve_bucket_work(dm, chunk, *buf);
+				if (m->opt_path == 0 && deriv_dir < 0) bw[k].stats = m->d_stats + k;
 			}
 			if (ns > 1) {
 				CUDA_OK(m, cudaEventRecord(m->ev_fork, st));
@@ -462,6 +512,12 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 			for (int k = 1; k < ns; k++) {
 				if ((rc = grow(m, &w.sortedx[k - 1], &w.sortedx_b[k - 1], sorted_work_bytes(dm, chunk)))) return rc;
 				sw[k] = carve_sorted_work(dm, w.sortedx[k - 1]);
+			}
+			if (m->opt_path == 0 && deriv_dir < 0 && m->d_stats && bucket_path_supported(dm) && !dm.ecell_off) {
+				// the counting sort reports what the fixed-capacity buckets WOULD have overflowed, so that a stream of batches that
+				// turns uniform again goes back to them
+				const int64_t bchunk = std::min<int64_t>(Q, std::max<int64_t>((int64_t)1 << 22, (int64_t)dm.L * 32));
+				for (int k = 0; k < ns; k++) { sw[k].stats = m->d_stats + k; sw[k].stats_cap = (int32_t)((double)bucket_capacity(dm, bchunk) * (double)chunk / (double)bchunk); }
 			}
 			if (ns > 1) {
 				// fork: the auxiliary streams start after everything already queued on the caller's stream
@@ -539,6 +595,105 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		m->launches += launch_mesh_gather(dm, (const double *)w.W, leaf + o, status + o, n, out + o * out_stride, out_stride, st);
 	}
 	CUDA_OK(m, cudaGetLastError());
+	return LOCO_OK;
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------------------------------
+// Three slots overlap H2D, kernels and D2H.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+// are used in place.  PAGEABLE caller buffers (std::vector, numpy: what a C++ caller of the facade hands in) would make every
+// cudaMemcpyAsync a synchronous, driver-staged copy; they are staged through per-slot page-locked buffers of the handle
+// instead, filled and drained by a few host threads, so that the copy engines still run asynchronously beside the kernels.
+bool is_page_locked(const void *p)
+{
+	if (!p) return true;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	const size_t nt = std::min<size_t>(std::min<unsigned>(8, std::max(1u, hw / 2)), bytes / ((size_t)4 << 20) + 1);
+	if (nt <= 1) { memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	const size_t part = ((bytes / nt) + 63) & ~(size_t)63;
+	for (size_t t = 1; t < nt; t++) {
+		const size_t o = t * part;
+		if (o >= bytes) break;
+		th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, std::min(part, bytes - o)); });
+	}
+	memcpy(dst, src, std::min(part, bytes));
+	for (auto &t : th) t.join();
+}
+
+int grow_pinned(loco_model *m, void **p, size_t *have, size_t need)
+{
+	if (need <= *have) return LOCO_OK;
+	if (*p) { CUDA_OK(m, cudaFreeHost(*p)); *p = nullptr; *have = 0; }
+	CUDA_OK(m, cudaHostAlloc(p, need, cudaHostAllocDefault));
+	*have = need;
+	return LOCO_OK;
+}
+
+int eval_batch_host(loco_model *m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, int deriv_dir)
+{
+	const DeviceModel &dm = m->dm;
+	const int64_t Dout = deriv_dir >= 0 ? 1 : dm.D;
+	// a slot's output is 128 MB for scalar functions; mesh-valued: 1 GB of results per slot, so that a chunk still holds
+	// enough queries per leaf for the tile kernels
+	const int64_t slot_bytes = Dout == 1 ? ((int64_t)128 << 20) : ((int64_t)1 << 30);
+	int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)4 << 20, slot_bytes / (Dout * 8)));
+	chunk = std::min(chunk, std::max<int64_t>(Q, 1));
+	const bool stage_in = !is_page_locked(q);
+	const bool stage_out = !is_page_locked(out) || !is_page_locked(leaf) || !is_page_locked(status);
+	struct Pending { int64_t o = 0, n = 0; } pending[kSlots];
+	auto drain = [&](int slot) {  // results of the slot's previous chunk: page-locked staging -> the caller's pageable buffers
+		const Pending &p = pending[slot];
+		if (!stage_out || p.n == 0) return;
+		Workspace &w = m->ws[slot];
+		parallel_memcpy(out + p.o * Dout, w.h_out, (size_t)p.n * Dout * 8);
+		if (leaf) memcpy(leaf + p.o, w.h_leaf, (size_t)p.n * 4);
+		if (status) memcpy(status + p.o, w.h_status, (size_t)p.n);
+		pending[slot].n = 0;
+	};
+	int rc;
+	int slot = 0;
+	for (int64_t o = 0; o < Q; o += chunk, slot = (slot + 1) % kSlots) {
+		const int64_t n = std::min(chunk, Q - o);
+		Workspace &w = m->ws[slot];
+		CUDA_OK(m, cudaStreamSynchronize(w.stream));  // the slot's previous chunk must have drained before its buffers are reused
+		drain(slot);
+		if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
+		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * Dout * 8))) return rc;
+		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
+		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
+		const double *src_q = q + o * dm.N;
+		if (stage_in) {
+			if ((rc = grow_pinned(m, &w.h_q, &w.h_q_b, (size_t)chunk * dm.N * 8))) return rc;
+			parallel_memcpy(w.h_q, src_q, (size_t)n * dm.N * 8);
+			src_q = (const double *)w.h_q;
+		}
+		CUDA_OK(m, cudaMemcpyAsync(w.q, src_q, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
+		if ((rc = eval_device(m, w, w.stream, false, (const double *)w.q, n, (double *)w.out, Dout, (int32_t *)w.leaf, (uint8_t *)w.status, deriv_dir))) return rc;
+		if (stage_out) {
+			if ((rc = grow_pinned(m, &w.h_out, &w.h_out_b, (size_t)chunk * Dout * 8))) return rc;
+			if ((rc = grow_pinned(m, &w.h_leaf, &w.h_leaf_b, (size_t)chunk * 4))) return rc;
+			if ((rc = grow_pinned(m, &w.h_status, &w.h_status_b, (size_t)chunk))) return rc;
+			CUDA_OK(m, cudaMemcpyAsync(w.h_out, w.out, (size_t)n * Dout * 8, cudaMemcpyDeviceToHost, w.stream));
+			if (leaf) CUDA_OK(m, cudaMemcpyAsync(w.h_leaf, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
+			if (status) CUDA_OK(m, cudaMemcpyAsync(w.h_status, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+			pending[slot].o = o; pending[slot].n = n;
+		} else {
+			CUDA_OK(m, cudaMemcpyAsync(out + o * Dout, w.out, (size_t)n * Dout * 8, cudaMemcpyDeviceToHost, w.stream));
+			if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
+			if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
+		}
+	}
+	for (int k = 0; k < kSlots; k++, slot = (slot + 1) % kSlots) {  // in submission order
+		CUDA_OK(m, cudaStreamSynchronize(m->ws[slot].stream));
+		drain(slot);
+	}
 	return LOCO_OK;
 }
 
@@ -665,9 +820,11 @@ void loco_free(loco_model_t *m)
 		if (m->ev_join[k]) cudaEventDestroy(m->ev_join[k]);
 	}
 	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+	if (m->h_stats) cudaFreeHost(m->h_stats);
 	for (int s = 0; s < kSlots; s++) {
 		Workspace &w = m->ws[s];
 		for (void *p : {w.q, w.out, w.leaf, w.status, w.W, w.truth, w.misc, w.sorted, w.sortedx[0], w.sortedx[1], w.sortedx[2], w.woff}) if (p) cudaFree(p);
+		for (void *p : {w.h_q, w.h_out, w.h_leaf, w.h_status}) if (p) cudaFreeHost(p);
 		if (w.stream) cudaStreamDestroy(w.stream);
 	}
 	delete m;
@@ -892,6 +1049,19 @@ int loco_model_get_values(const loco_model_t *m, int64_t row0, int64_t n, double
 	return LOCO_OK;
 }
 
+int loco_model_get_value_columns(const loco_model_t *m, int64_t col0, int64_t n, double *out)
+{
+	if (!m || !out) return fail(m, LOCO_ERR_INVALID, "null argument");
+	if (col0 < 0 || n < 0 || col0 + n > m->dm.D) return fail(m, LOCO_ERR_RANGE, "value component out of range");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	if (n == 0) return LOCO_OK;
+	CUDA_OK(m, cudaMemcpy2D(out, (size_t)n * sizeof(double), m->d_values + col0, (size_t)dm.value_stride * sizeof(double),
+	                        (size_t)n * sizeof(double), (size_t)dm.R, cudaMemcpyDeviceToHost));
+	return LOCO_OK;
+}
+
 // ---- hot path ---------------------------------------------------------------------------------------------
 int loco_eval_batch_device(loco_model_t *m, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status, void *cuda_stream)
 {
@@ -906,30 +1076,7 @@ int loco_eval_batch(loco_model_t *m, const double *q, int64_t Q, double *out, in
 	if (!m || (Q > 0 && (!q || !out))) return fail(m, LOCO_ERR_INVALID, "null argument");
 	NEED_DEVICE(m);
 	CUDA_OK(m, cudaSetDevice(m->device));
-	const DeviceModel &dm = m->dm;
-	// three slots overlap H2D, kernels and D2H; a slot's output is 128 MB for scalar functions
-	// mesh-valued: 1 GB of results per slot, so that a chunk still holds enough queries per leaf for the tile kernels
-	const int64_t slot_bytes = dm.D == 1 ? ((int64_t)128 << 20) : ((int64_t)1 << 30);
-	int64_t chunk = std::max<int64_t>(1, std::min<int64_t>((int64_t)4 << 20, slot_bytes / ((int64_t)dm.D * 8)));
-	chunk = std::min(chunk, std::max<int64_t>(Q, 1));
-	int rc;
-	int slot = 0;
-	for (int64_t o = 0; o < Q; o += chunk, slot = (slot + 1) % kSlots) {
-		const int64_t n = std::min(chunk, Q - o);
-		Workspace &w = m->ws[slot];
-		CUDA_OK(m, cudaStreamSynchronize(w.stream));  // the slot's previous chunk must have drained before its buffers are reused
-		if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
-		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * dm.D * 8))) return rc;
-		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
-		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
-		CUDA_OK(m, cudaMemcpyAsync(w.q, q + o * dm.N, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
-		if ((rc = eval_device(m, w, w.stream, false, (const double *)w.q, n, (double *)w.out, dm.D, (int32_t *)w.leaf, (uint8_t *)w.status))) return rc;
-		CUDA_OK(m, cudaMemcpyAsync(out + o * dm.D, w.out, (size_t)n * dm.D * 8, cudaMemcpyDeviceToHost, w.stream));
-		if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
-		if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
-	}
-	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamSynchronize(m->ws[s].stream));
-	return LOCO_OK;
+	return eval_batch_host(m, q, Q, out, leaf, status, -1);
 }
 
 int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t Q, double *ring, int64_t ring_queries, double *checksum,
@@ -989,6 +1136,32 @@ int loco_eval_batch_ring_device(loco_model_t *m, const double *q, int64_t Q, dou
 	return LOCO_OK;
 }
 
+int loco_eval_batch_ring(loco_model_t *m, const double *q, int64_t Q, int64_t ring_queries, double *checksum, int32_t *leaf, uint8_t *status)
+{
+	if (!m || (Q > 0 && (!q || !checksum)) || ring_queries < 0) return fail(m, LOCO_ERR_INVALID, "null argument");
+	NEED_DEVICE(m);
+	CUDA_OK(m, cudaSetDevice(m->device));
+	const DeviceModel &dm = m->dm;
+	if (Q == 0) return LOCO_OK;
+	if (ring_queries == 0) ring_queries = std::max<int64_t>(mesh_mma_tile_queries(), std::min<int64_t>(Q, ((int64_t)16 << 30) / ((int64_t)dm.value_stride * 8)));
+	Workspace &w = m->ws[1];  // slot 1: slot 0 is the device-side call's workspace
+	cudaStream_t st = w.stream;
+	int rc;
+	if ((rc = grow(m, &w.q, &w.q_b, (size_t)Q * dm.N * 8))) return rc;
+	if ((rc = grow(m, &w.out, &w.out_b, (size_t)ring_queries * dm.value_stride * 8))) return rc;
+	if ((rc = grow(m, &w.truth, &w.truth_b, (size_t)Q * 8))) return rc;      // the checksums
+	if ((rc = grow(m, &w.W, &w.W_b, (size_t)Q * 5))) return rc;              // leaf + status for the caller
+	int32_t *d_leaf = (int32_t *)w.W;
+	uint8_t *d_status = (uint8_t *)w.W + (size_t)Q * 4;
+	CUDA_OK(m, cudaMemcpyAsync(w.q, q, (size_t)Q * dm.N * 8, cudaMemcpyHostToDevice, st));
+	if ((rc = loco_eval_batch_ring_device(m, (const double *)w.q, Q, (double *)w.out, ring_queries, (double *)w.truth, d_leaf, d_status, st))) return rc;
+	CUDA_OK(m, cudaMemcpyAsync(checksum, w.truth, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+	if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf, d_leaf, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+	if (status) CUDA_OK(m, cudaMemcpyAsync(status, d_status, (size_t)Q, cudaMemcpyDeviceToHost, st));
+	CUDA_OK(m, cudaStreamSynchronize(st));
+	return LOCO_OK;
+}
+
 // ---- derivative ---------------------------------------------------------------------------------------------------
 int loco_eval_deriv_batch_device(loco_model_t *m, const double *q, int64_t Q, int32_t direction, double *out, int32_t *leaf, uint8_t *status,
                                  void *cuda_stream)
@@ -1008,26 +1181,7 @@ int loco_eval_deriv_batch(loco_model_t *m, const double *q, int64_t Q, int32_t d
 	if (direction < 0 || direction >= m->flat.N) return fail(m, LOCO_ERR_RANGE, "derivative direction out of range");
 	NEED_DEVICE(m);
 	CUDA_OK(m, cudaSetDevice(m->device));
-	const DeviceModel &dm = m->dm;
-	const int64_t chunk = std::min<int64_t>((int64_t)4 << 20, std::max<int64_t>(Q, 1));
-	int rc;
-	int slot = 0;
-	for (int64_t o = 0; o < Q; o += chunk, slot = (slot + 1) % kSlots) {
-		const int64_t n = std::min(chunk, Q - o);
-		Workspace &w = m->ws[slot];
-		CUDA_OK(m, cudaStreamSynchronize(w.stream));
-		if ((rc = grow(m, &w.q, &w.q_b, (size_t)chunk * dm.N * 8))) return rc;
-		if ((rc = grow(m, &w.out, &w.out_b, (size_t)chunk * 8))) return rc;
-		if ((rc = grow(m, &w.leaf, &w.leaf_b, (size_t)chunk * 4))) return rc;
-		if ((rc = grow(m, &w.status, &w.status_b, (size_t)chunk))) return rc;
-		CUDA_OK(m, cudaMemcpyAsync(w.q, q + o * dm.N, (size_t)n * dm.N * 8, cudaMemcpyHostToDevice, w.stream));
-		if ((rc = eval_device(m, w, w.stream, false, (const double *)w.q, n, (double *)w.out, 1, (int32_t *)w.leaf, (uint8_t *)w.status, direction))) return rc;
-		CUDA_OK(m, cudaMemcpyAsync(out + o, w.out, (size_t)n * 8, cudaMemcpyDeviceToHost, w.stream));
-		if (leaf) CUDA_OK(m, cudaMemcpyAsync(leaf + o, w.leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, w.stream));
-		if (status) CUDA_OK(m, cudaMemcpyAsync(status + o, w.status, (size_t)n, cudaMemcpyDeviceToHost, w.stream));
-	}
-	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamSynchronize(m->ws[s].stream));
-	return LOCO_OK;
+	return eval_batch_host(m, q, Q, out, leaf, status, direction);
 }
 
 // ---- error check ----------------------------------------------------------------------------------------------
@@ -1156,6 +1310,62 @@ int loco_error_check_generated_device(loco_model_t *m, int64_t ppl, uint64_t see
 	return LOCO_OK;
 }
 
+// ---- multi-GPU result exchange: peer-mapped buffers + copy-engine pushes ------------------------------------------------
+#define CUDA_OK0(expr)                                                                                        \
+	do {                                                                                                      \
+		cudaError_t _e = (expr);                                                                              \
+		if (_e != cudaSuccess) return fail(nullptr, LOCO_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(_e)); \
+	} while (0)
+
+int loco_peer_buffer_create(int device, size_t bytes, void **dptr, unsigned char handle[64])
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+	if (!dptr || !handle || bytes == 0) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	CUDA_OK0(cudaSetDevice(device));
+	void *p = nullptr;
+	CUDA_OK0(cudaMalloc(&p, bytes));
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) { cudaFree(p); return fail(nullptr, LOCO_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+	memcpy(handle, &h, 64);
+	*dptr = p;
+	return LOCO_OK;
+}
+
+int loco_peer_buffer_open(int device, const unsigned char handle[64], void **dptr)
+{
+	if (!dptr || !handle) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	CUDA_OK0(cudaSetDevice(device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CUDA_OK0(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return LOCO_OK;
+}
+
+int loco_peer_buffer_close(int device, void *dptr)
+{
+	if (!dptr) return LOCO_OK;
+	CUDA_OK0(cudaSetDevice(device));
+	CUDA_OK0(cudaIpcCloseMemHandle(dptr));
+	return LOCO_OK;
+}
+
+int loco_peer_buffer_free(int device, void *dptr)
+{
+	if (!dptr) return LOCO_OK;
+	CUDA_OK0(cudaSetDevice(device));
+	CUDA_OK0(cudaFree(dptr));
+	return LOCO_OK;
+}
+
+int loco_peer_copy_async(void *dst, const void *src, size_t bytes, void *cuda_stream)
+{
+	if (bytes == 0) return LOCO_OK;
+	if (!dst || !src) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	CUDA_OK0(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+	return LOCO_OK;
+}
+
 // ---- options ---------------------------------------------------------------------------------------------------
 int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 {
@@ -1166,6 +1376,12 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 	if (!strcmp(name, "uniform")) { m->opt_uniform = value; m->dm.tensor_uniform = (m->flat.tensor_uniform && value) ? 1 : 0; return LOCO_OK; }  // 0: four separate factor evaluations
 	if (!strcmp(name, "overlap")) { m->opt_overlap = value; return LOCO_OK; }  // streams the chunks of the sorted path are dealt over (1..4, default 2)
 	if (!strcmp(name, "chunk")) { m->opt_chunk = value; return LOCO_OK; }  // queries per L2-resident chunk of the sorted path (0 = auto)
+	if (!strcmp(name, "leaf_poly")) {  // 1 (default): scalar functions on single-piece tensor leaves evaluate the leaf's polynomial, 0: factor / contraction form
+		m->opt_leaf_poly = value;
+		m->dm.tl_poly = (value && m->dm.tp_stride > 0) ? m->d_tl_poly : nullptr;
+		return LOCO_OK;
+	}
+	if (!strcmp(name, "adaptive")) { m->opt_adaptive = value; if (!value) m->skewed = false; return LOCO_OK; }  // 0: path 0 never leaves the leaf buckets
 	if (!strcmp(name, "fused_errgen")) { m->opt_fused_errgen = value; return LOCO_OK; }  // 0: the three-kernel form of loco_error_check_generated_device
 	if (!strcmp(name, "ecell_poly")) {  // 1: polynomial form of the evaluation cells no knot crosses (see loco_cellpoly.h), 0: term lists
 		m->dm.epoly_idx = (value && m->dm.ecell_off) ? m->d_epoly_idx : nullptr;

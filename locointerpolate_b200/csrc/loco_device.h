@@ -60,12 +60,21 @@ struct DeviceModel {
 	int32_t tensor_F, tensor_K, tl_stride, tl_voff, tensor_uniform;
 	const double *tl_block;           // [L * tl_stride]
 	const float *tl_vals_f32;         // [L * F^N] fp32 copy of the leaf values in tensor order (optional fp32 mode, D == 1)
+	// per-leaf polynomial form (D == 1, Flat::tensor_poly; nullptr: not built or switched off by option "leaf_poly"):
+	//   [N x (mid_d, 1/halfwidth_d) | F^N coefficients, dimension 0 fastest], tp_stride doubles per leaf;
+	//   value(x) = sum_j coef[j] prod_d t_d^(j_d),  t_d = (x_d - mid_d) / halfwidth_d in [-1, 1] inside the leaf
+	const double *tl_poly;
+	int32_t tp_stride;
 	const int32_t *tl_row;            // [L * F^N] value rows in tensor order
 	// locate grid (Flat::lut): lut == nullptr disables it
 	const uint32_t *lut;
 	const double *lut_bounds;
 	int32_t lut_bits[kMaxN], lut_boff[kMaxN];
 	double lut_lo[kMaxN], lut_inv[kMaxN];   // estimate of the grid cell: (x - lo) * inv, then exact comparisons
+	// dimensions whose grid boundaries are EXACTLY lo + i*h with h a power of two (every bootstrap grid): the boundary next to
+	// the estimate is formed by one exact fma instead of two table loads
+	double lut_h[kMaxN];
+	uint32_t lut_uniform_mask;
 	// folded tensor leaves (Flat::fold_*): value rows after merging digits that share rows
 	const int32_t *fold_off;          // [L+1]
 	const int32_t *fold_row;
@@ -160,6 +169,7 @@ int launch_update_mterm_wv(const DeviceModel &m, double *mterm_wv, cudaStream_t 
 int launch_update_eterm_wv(const DeviceModel &m, double *eterm_wv, cudaStream_t st);
 int launch_update_epoly(const DeviceModel &m, const int32_t *epoly_cell, int32_t n_epoly, double *epoly, cudaStream_t st);
 int launch_update_tensor_vals(const DeviceModel &m, double *tl_block, float *tl_vals_f32, cudaStream_t st);
+int launch_update_tensor_poly(const DeviceModel &m, double *tl_poly, int32_t tp_stride, cudaStream_t st);
 int launch_eval_scalar_tensor_direct(const DeviceModel &m, bool in_cube, const double *q, int64_t Q, double *out, int32_t *leaf, uint8_t *status,
                                      cudaStream_t st);
 int launch_sort_by_leaf(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, const SortWork &w, int tile_q,
@@ -186,7 +196,14 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
                              int sm_count, cudaStream_t st);
 
 // ---- L2-resident sorted chunks (loco_sorted.cu)
+// Skew statistics of a workspace slot (host-mapped, written by ONE thread per chunk, read by the host between calls):
+// queries that did not fit / would not have fit their leaf's fixed-capacity bucket, and queries seen.  eval_device() uses
+// them to pick the leaf-bucket path (uniform batches) or the exact counting sort (skewed batches) for the NEXT call.
+struct SkewStats { long long overflow, total; };
+
 struct SortedWork {
+	SkewStats *stats;  // may be null
+	int32_t stats_cap; // bucket capacity the overflow is counted against
 	int32_t *count;    // [L] histogram (zero between chunks)
 	int32_t *cursor;   // [L+1] bucket cursors; [L] = number of records of the chunk
 	unsigned *done;    // arrival counter of the count kernel
@@ -200,6 +217,7 @@ int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64
 
 // ---- single-pass fixed-capacity leaf buckets (loco_bucket.cu)
 struct BucketWork {
+	SkewStats *stats;  // may be null
 	int32_t *count;    // [L] queries that asked for a slot in the leaf's bucket (zero between chunks)
 	int32_t *n_ovf;    // number of overflow entries
 	int32_t *ovf;      // [chunk] query indices whose bucket was full

@@ -45,9 +45,13 @@ __global__ void __launch_bounds__(256, 2) error_check_generated_kernel(DeviceMod
 	const int32_t leaf = (int32_t)(blockIdx.x / cpl);
 	const int64_t i0 = (int64_t)(blockIdx.x % cpl) * span, i1 = min(ppl, i0 + span);
 	if (m.any_leaf_status && m.leaf_status[leaf] != ST_OK) return;  // the cell reports an error for every point: nothing to compare
+	// the leaf's polynomial block where the model has one (every generated point lies inside the leaf box), else the classic block
+	const bool poly = m.tl_poly != nullptr;
+	const int blk_doubles = poly ? m.tp_stride : m.tl_stride;
+	const double *src = poly ? m.tl_poly + (int64_t)leaf * m.tp_stride : m.tl_block + (int64_t)leaf * m.tl_stride;
 	double *blk = s_mem;
-	double *ac = s_mem + m.tl_stride, *as = ac + NT * n_terms;
-	for (int e = threadIdx.x; e < m.tl_stride; e += blockDim.x) blk[e] = m.tl_block[(int64_t)leaf * m.tl_stride + e];
+	double *ac = s_mem + blk_doubles, *as = ac + NT * n_terms;
+	for (int e = threadIdx.x; e < blk_doubles; e += blockDim.x) blk[e] = src[e];
 	for (int e = threadIdx.x; e < NT * n_terms; e += blockDim.x) {
 		double sp, cp;
 		sincos(phase[e], &sp, &cp);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256, 2) error_check_generated_kernel(DeviceMod
 			}
 			truth += fi;
 		}
-		const double approx = tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
+		const double approx = poly ? tensor_leaf_value<NT, CUBIC, EXACT>(m, nullptr, blk, leaf, x) : tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
 		const double e = fabs(approx - truth);
 		sp |= !((e - threshold) <= 0);
 		const unsigned long long bits = (unsigned long long)__double_as_longlong(e);
@@ -124,7 +128,7 @@ void run(const DeviceModel &m, int64_t ppl, uint64_t seed, const double *amp, co
 	int cpl = (int)std::max<int64_t>(1, std::min<int64_t>((want + m.L - 1) / m.L, (ppl + 1023) / 1024));
 	const int64_t span = (ppl + cpl - 1) / cpl;
 	cpl = (int)((ppl + span - 1) / span);
-	const size_t smem = ((size_t)m.tl_stride + 2 * (size_t)NT * n_terms) * sizeof(double);
+	const size_t smem = ((size_t)std::max(m.tl_stride, m.tp_stride) + 2 * (size_t)NT * n_terms) * sizeof(double);
 	auto kern = error_check_generated_kernel<NT, CUBIC, EXACT>;
 	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	LOCO_KERNEL("error_check_generated", st);
@@ -137,7 +141,7 @@ void run(const DeviceModel &m, int64_t ppl, uint64_t seed, const double *amp, co
 bool error_check_generated_fused_supported(const DeviceModel &m, int n_terms)
 {
 	return m.D == 1 && m.tensor_F > 0 && m.N >= 1 && m.N <= kMaxTemplateN && n_terms >= 0 && n_terms <= kMaxTruthTerms &&
-	       ((size_t)m.tl_stride + 2 * (size_t)m.N * n_terms) * sizeof(double) <= 160 * 1024;
+	       ((size_t)std::max(m.tl_stride, m.tp_stride) + 2 * (size_t)m.N * n_terms) * sizeof(double) <= 160 * 1024;
 }
 
 int launch_error_check_generated_fused(const DeviceModel &m, int64_t ppl, uint64_t seed, const double *amp, const double *phase, int n_terms, double threshold,

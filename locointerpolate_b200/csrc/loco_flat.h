@@ -111,6 +111,8 @@ struct Flat {
 	// structure with the same F; the generic term lists above stay valid either way.
 	int32_t tensor_F = 0;
 	int32_t tensor_K = 0;                 // F^N
+	bool tensor_poly = false;             // every leaf lies inside ONE polynomial piece of each of its F per-dimension basis functions (no knot strictly
+	                                      // inside the leaf box): the interpolant on the leaf is a single tensor-product polynomial
 	bool tensor_uniform = false;          // cubic: in every leaf and dimension the 4 centres are spaced by exactly support/2 (one uniform knot vector)
 	std::vector<double> tl_center;        // [L * N * F] ascending per dimension
 	std::vector<double> tl_rcp;           // [L * N]     support (or 1/support when exact_rcp)

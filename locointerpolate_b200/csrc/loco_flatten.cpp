@@ -496,6 +496,17 @@ Status flatten(const Graph &g, Flat *out)
 					uni = uni && f.leaf_lo[(size_t)l * N + i] == c[1] && f.leaf_hi[(size_t)l * N + i] == c[2];
 				}
 			f.tensor_uniform = uni;
+			// single polynomial piece per leaf: no knot of any of the leaf's one-dimensional basis functions strictly inside the leaf box
+			bool poly = true;
+			for (int64_t l = 0; l < L && poly; l++)
+				for (int i = 0; i < N && poly; i++) {
+					const double *c = &f.tl_center[((size_t)l * N + i) * F];
+					const double r = f.tl_rcp[(size_t)l * N + i], sup = f.exact_rcp ? 1.0 / r : r;
+					const double lo = f.leaf_lo[(size_t)l * N + i], hi = f.leaf_hi[(size_t)l * N + i];
+					if (!(hi > lo)) poly = false;
+					for (int j = 0; j < F && poly; j++) poly = cubic ? !knot_inside<true>(c[j], sup, lo, hi) : !knot_inside<false>(c[j], sup, lo, hi);
+				}
+			f.tensor_poly = poly;
 		}
 		else { f.tl_center.clear(); f.tl_rcp.clear(); f.tl_slot.clear(); f.tl_row.clear(); }
 		// ---- fold digits whose exchange never changes the value row (see loco_flat.h)

@@ -107,11 +107,14 @@ __global__ void __launch_bounds__(256) sorted_count_kernel(DeviceModel m, const 
 constexpr int kScanThreads = 1024;
 constexpr int kScanSeg = 32768;  // leaves per pass
 __device__ __forceinline__ int scan_pad(int e) { return e + (e >> 5); }
-__global__ void __launch_bounds__(kScanThreads) sorted_scan_kernel(int32_t *count, int32_t *cursor, int32_t L)
+__global__ void __launch_bounds__(kScanThreads) sorted_scan_kernel(int32_t *count, int32_t *cursor, int32_t L, SkewStats *stats, int32_t stats_cap)
 {
 	extern __shared__ int s_hist[];  // [kScanSeg + kScanSeg / 32]
 	__shared__ int warp_tot[kScanThreads / 32];
+	__shared__ unsigned long long s_over;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_over = 0ull;
+	long long over = 0;  // queries beyond a fixed-capacity bucket of stats_cap slots (skew statistic)
 	int carry = 0;
 	for (int base = 0; base < L; base += kScanSeg) {
 		const int n = min(kScanSeg, L - base);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kScanThreads) sorted_scan_kernel(int32_t *coun
 		const int per = (n + kScanThreads - 1) / kScanThreads;
 		const int l0 = min((int)threadIdx.x * per, n), l1 = min(l0 + per, n);
 		int mine = 0;
-		for (int l = l0; l < l1; l++) mine += s_hist[scan_pad(l)];
+		for (int l = l0; l < l1; l++) { const int c = s_hist[scan_pad(l)]; mine += c; over += max(0, c - stats_cap); }
 		int incl = mine;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
@@ -154,6 +157,11 @@ __global__ void __launch_bounds__(kScanThreads) sorted_scan_kernel(int32_t *coun
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) cursor[L] = carry;
+	if (stats) {
+		if (over) atomicAdd(&s_over, (unsigned long long)over);
+		__syncthreads();
+		if (threadIdx.x == 0) { stats->overflow += (long long)s_over; stats->total += carry; }
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -259,6 +267,9 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 					const char *val_bytes = reinterpret_cast<const char *>(m.tl_vals_f32 + (int64_t)nleaf * m.tensor_K);
 					for (int o = 0; o < m.tl_voff * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk_bytes + o));
 					for (int o = 0; o < m.tensor_K * 4; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(val_bytes + o));
+				} else if (m.tl_poly) {
+					const char *pb = reinterpret_cast<const char *>(m.tl_poly + (int64_t)nleaf * m.tp_stride);
+					for (int o = 0; o < m.tp_stride * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
 				} else
 				for (int o = 0; o < m.tl_stride * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk_bytes + o));
 			}
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(256, (NT > 0 && NT <= 3) ? 3 : 2) sorted_eval_
 		double r = 0.0;
 		if constexpr (TENSOR) {
 			if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf * m.tl_stride, m.tl_vals_f32 + (int64_t)leaf * m.tensor_K, x);
-			else r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, m.tl_block + (int64_t)leaf * m.tl_stride, x);
+			else r = tensor_leaf_value<NT, CUBIC, EXACT>(m, nullptr, m.tl_poly ? m.tl_poly + (int64_t)leaf * m.tp_stride : nullptr, leaf, x);
 		} else {
 			// LCSample::getInterpolationWeight / newFromWeightedSum over the leaf's term list, as in eval_scalar_direct_kernel,
 			// with weight_ * val pre-multiplied per term (term_wv)
@@ -318,7 +329,7 @@ void run_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, 
 	{ LOCO_KERNEL("sorted_count", st);
 	sorted_count_kernel<NT><<<(unsigned)((Q + 256 * kCountItems - 1) / (256 * kCountItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
 	LOCO_KERNEL("sorted_scan", st);
-	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, sort_buckets(m));
+	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, sort_buckets(m), w.stats, w.stats_cap);
 }
 template <int NT>
 void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortedWork &w, cudaStream_t st)
@@ -352,6 +363,7 @@ size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk)
 SortedWork carve_sorted_work(const DeviceModel &m, void *base)
 {
 	SortedWork w;
+	w.stats = nullptr; w.stats_cap = 0x7fffffff;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
 	w.count = p; p += sort_buckets(m);
 	w.cursor = p; p += sort_buckets(m) + 1;

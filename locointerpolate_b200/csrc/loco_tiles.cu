@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(TILE_Q) eval_tensor_tiles_kernel(DeviceModel m
 		}
 		// ---- this tile
 		if (need_wait) { mbar_wait(&bar[buf], (phases >> buf) & 1u); phases ^= 1u << buf; need_wait = false; }
-		const double r = tensor_eval_scalar<NT, CUBIC, EXACT>(m, S_BLK(buf), x);
+		const double r = m.tl_poly ? tensor_leaf_value<NT, CUBIC, EXACT>(m, nullptr, m.tl_poly + (int64_t)leaf * m.tp_stride, leaf, x)
+		                           : tensor_eval_scalar<NT, CUBIC, EXACT>(m, S_BLK(buf), x);
 		if (active) out[qi] = r;
 		if (next_changes) {
 			__syncthreads();  // all reads of s_blk[buf] are done before it can be refilled (two leaves from now)

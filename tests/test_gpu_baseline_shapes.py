@@ -155,10 +155,15 @@ def test_c3_shape_4d_linear_mesh_d30000():
     cols = np.sort(rng.choice(D, 64, replace=False))
     cols[0], cols[-1] = 0, D - 1
 
-    def synthetic(ids):  # include/loco_b200.h: v[row][j] = sin(0.37 j + 0.61 row + seed) + 0.001 (j % 97)
-        r = rows[ids].astype(np.float64)[:, None]
-        return np.sin(0.37 * cols[None, :] + 0.61 * r + seed) + 0.001 * (cols[None, :] % 97)
-    assert np.allclose(mesh.get_values(int(rows[5]), 1)[0][cols], synthetic(np.array([5]))[0], atol=1e-13)
+    # the sampled columns of the device's table (the device forms sin(0.37 j + 0.61 row + seed) with fused multiply-adds, so a
+    # host recomputation of the ARGUMENT differs by an ulp of ~1e4, i.e. ~2e-12 in the value: read the table back instead)
+    R = mesh.info["n_value_rows"]
+    tab = np.concatenate([mesh.get_values(r0, min(512, R - r0))[:, cols] for r0 in range(0, R, 512)])
+    j = cols[None, :]
+    assert np.abs(tab - (np.sin(0.37 * j + 0.61 * np.arange(R)[:, None] + seed) + 0.001 * (j % 97))).max() < 1e-10
+
+    def synthetic(ids):
+        return tab[rows[ids]]
     q = rng.random((Q, N)) * 1.0000004 - 0.0000002
     q[:256] = np.round(q[:256] * 8) / 8   # on sample positions / split planes
     q[256:260, 1] = -0.5
@@ -392,7 +397,7 @@ def test_save_proto_follows_set_values(tmp_path):
     o_out, _, _, scale = orc.eval(q)
     assert_values_close(want, o_out, scale)
     # mesh-valued, table filled on the device only: the file carries the synthetic table
-    mesh = capi.Model.bootstrap(2, capi.LINEAR, 2, 6, True, fn=None, device=0)
+    mesh = capi.Model.bootstrap(2, capi.LINEAR, 2, 6, True, fn=lambda p: np.arange(6) + float(p.sum()), device=0)
     mesh.fill_values_synthetic(0.75)
     p2 = str(tmp_path / "b.pb")
     mesh.save_proto(p2)
@@ -416,3 +421,47 @@ def test_error_check_nan_component_is_sticky():
     assert np.isnan(err[leaf[17]]) and split[leaf[17]] == 1
     others = np.arange(m.L) != leaf[17]
     assert (err[others] <= 1e-13).all() and (split[others] == 0).all()
+
+
+def test_adaptive_dispatch_between_buckets_and_counting_sort():
+    """Automatic path selection for big scalar batches on tensor-product leaves: uniform batches take the single-pass leaf
+    buckets; once the batches seen so far overflow the buckets' capacity (skewed batches) the next calls take the exact
+    counting sort, and go back when the batches turn uniform again.  Decided from counters the kernels keep (no
+    synchronisation), so a switch takes effect a call later; results are the same on every path."""
+    torch = _torch()
+    m = capi.Model.bootstrap(3, capi.CUBIC, 4, 1, True, fn=lambda p: 1 + float(np.sin(3 * p).sum()), device=0)
+    Q = 2_000_000
+    gen = torch.Generator("cuda").manual_seed(31)
+    uniform = torch.rand((Q, 3), dtype=torch.float64, device="cuda", generator=gen)
+    skewed = uniform.clone()
+    skewed[::2] = skewed[::2] * 0.1 + 0.45   # half of the batch in 0.1 % of the domain
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(tq):
+        out = torch.empty(Q, dtype=torch.float64, device="cuda")
+        leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
+        status = torch.empty(Q, dtype=torch.uint8, device="cuda")
+        m.profile_begin()
+        m.eval_device(tq.data_ptr(), Q, out.data_ptr(), leaf.data_ptr(), status.data_ptr(), st)
+        prof = m.profile_end()   # synchronises: the counters of this call are visible to the next one
+        return out, leaf, prof
+
+    m.set_option("path", 1)
+    ref_u, leaf_u, _ = run(uniform)
+    ref_s, leaf_s, _ = run(skewed)
+    m.set_option("path", 0)
+    o, l, prof = run(uniform)
+    assert "bucket_eval" in prof and torch.equal(o, ref_u) and torch.equal(l, leaf_u)
+    o, l, prof = run(skewed)                      # decided before its own statistics exist: still the buckets (overflow list)
+    assert "bucket_eval" in prof and torch.equal(o, ref_s) and torch.equal(l, leaf_s)
+    o, l, prof = run(skewed)                      # the previous call overflowed: counting sort
+    assert "sorted_eval" in prof and "bucket_eval" not in prof, prof
+    assert torch.equal(o, ref_s) and torch.equal(l, leaf_s)
+    o, l, prof = run(uniform)                     # the previous (sorted) call was still skewed
+    assert "sorted_eval" in prof and torch.equal(o, ref_u)
+    o, l, prof = run(uniform)                     # ... and the last one was uniform: back to the buckets
+    assert "bucket_eval" in prof and torch.equal(o, ref_u)
+    m.set_option("adaptive", 0)
+    o, l, prof = run(skewed)
+    o, l, prof = run(skewed)
+    assert "bucket_eval" in prof and torch.equal(o, ref_s)

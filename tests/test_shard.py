@@ -77,3 +77,56 @@ def test_sharded_eval_and_error_reduce_gloo(world, Q):
     assert np.array_equal(got["err"], o_err, equal_nan=True) and np.array_equal(got["split"], o_split)
     if Q > 300:
         assert np.isnan(got["err"]).sum() == 1 and got["split"][np.isnan(got["err"])].all()
+
+
+def _exchange_worker(rank, world, port, n_batches, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ex = shard.RotatingExchange(n, torch.float64, "cpu")
+        assert ex.transport == "p2p"
+        ex.warm()
+
+        def shard_of(b, r):   # what rank r "evaluates" for batch b
+            return torch.arange(n, dtype=torch.float64) + 1000.0 * b + 10.0 * r
+
+        ok = True
+        for epoch in range(2):   # drain() ends an epoch; the exchange is reusable (warm-up, then the timed region)
+            checked = 0
+            for b in range(n_batches):
+                out = ex.out_buffer(b)
+                out.copy_(shard_of(b + 100 * epoch, rank))
+                ex.submit(b)
+                done = b - (world - 1)   # every shard of this batch has been shipped by now (skew: rank r ships batch b at step b + r)
+                if done >= 0 and ex.consumer(done) == rank:
+                    g = ex.gathered(done)
+                    ok &= all(torch.equal(g[r], shard_of(done + 100 * epoch, r)) for r in range(world))
+                    checked += 1
+            ex.drain()
+            for b in range(max(0, n_batches - (world - 1)), n_batches):
+                if ex.consumer(b) == rank and b >= n_batches - 2 * world:
+                    g = ex.gathered(b)
+                    ok &= all(torch.equal(g[r], shard_of(b + 100 * epoch, r)) for r in range(world))
+                    checked += 1
+            ret[(rank, epoch)] = (bool(ok), checked)
+        ex.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_batches", [(2, 7), (3, 8), (3, 2), (4, 9)])
+def test_rotating_exchange_schedule(world, n_batches):
+    """RotatingExchange (the bench's exchange step for scalar results): batch b is gathered on rank b % world, rank r ships
+    batch b at step b + r so that every step is a permutation; point-to-point transport over gloo stands in for the
+    copy-engine pushes."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, port, n_batches, 257, ret), nprocs=world, join=True)
+        res = dict(ret)
+    assert len(res) == 2 * world
+    total = 0
+    for (rank, epoch), (ok, checked) in res.items():
+        assert ok, (rank, epoch)
+        total += checked
+    assert total == 2 * n_batches   # every batch was checked on its consumer, in both epochs
