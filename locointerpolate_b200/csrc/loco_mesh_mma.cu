@@ -15,13 +15,17 @@
 //
 // The CTA is warp-specialised; nothing in the steady state uses __syncthreads:
 //   * warps 8-9 (producers, one lane per query of the tile): per item compute the query's N*F one-dimensional factors
-//     and its table of low-dimension products; per step wait for a free stage, form the stage's weights
-//     w[kk][q] = low[k % LOWK][q] * prod_{d >= LOWD} f_d[digit_d(k)][q] (LCSample::getInterpolationWeight on a
-//     unit-weight tensor grid) in shared memory and (producer 0) start the TMA bulk copies of the stage's 16 value-row segments;
-//     an mbarrier per stage collects "weights written" + the TMA transaction bytes.
-//   * warps 0-7 (consumers): wait for the stage, run 4x4 DMMA tiles per warp (32 queries x 32 components), release
-//     the stage with one arrival per warp, and after the last stage of a chunk write each output element once with
-//     128-bit streaming stores.
+//     and the table of its low-dimension products low[kl][q] (kl < lowK <= 16 rows: ONE stage of value rows); the weight of
+//     row k = kl + lowK * h is w = low[kl][q] * high_h[q] with high_h = prod_{d >= LOWD} f_d[digit_d(h)][q]
+//     (LCSample::getInterpolationWeight on a unit-weight tensor grid).  low[][] is written ONCE per item; per stage the
+//     producers wait for a free stage, write the stage's 64 high factors and (producer 0) start the TMA bulk copies of the
+//     stage's value-row segments; an mbarrier per stage collects "factors written" + the TMA transaction bytes.
+//     (Round 1 wrote all 16 x 64 weights of every stage: 16 dependent fp64 multiplies per producer lane and stage, queued on
+//     the fp64 pipe behind the consumers' DMMAs -- the consumers waited for the producers 38 % of the time.)
+//   * warps 0-7 (consumers): wait for the stage, scale their A fragments (low[][] of the item) by the stage's high factor
+//     of the fragment's query -- the same product low * high the producers used to form --, run 4x4 DMMA tiles per warp
+//     (32 queries x 32 components), release the stage with one arrival per warp, and after the last stage of a chunk write
+//     each output element once with 128-bit streaming stores.
 // Items are ordered chunk-group major and dealt round-robin to the CTAs, so that at any time all CTAs read the same
 // slice of the value table (it stays L2 resident: the table is read from HBM about once per batch).
 #include <algorithm>
@@ -38,7 +42,7 @@ namespace {
 constexpr int MM_Q = 64;      // queries per tile
 constexpr int MM_D = 128;     // value components per chunk
 constexpr int MM_K = 16;      // value rows per stage
-constexpr int MM_NS_MULTI = 3; // stages in flight when a chunk needs several stages (2 CTAs of ~98 KB per SM)
+constexpr int MM_NS_MULTI = 4; // stages in flight when a chunk needs several stages (2 CTAs of ~100 KB per SM)
 constexpr int MM_NS_ONE = 4;   // ... when all K <= 16 rows fit one stage: the weights are per item, a stage is value rows only
 constexpr bool MM_TMA_STORE = false;  // results through shared memory + TMA bulk stores (measured: no gain over direct 256-bit stores, costs a stage)
 constexpr int MM_STG_LD = 40;  // row stride (doubles) of a warp's 8 x 32 result staging block: conflict-free 128-bit stores, 16-byte aligned rows
@@ -53,7 +57,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc, row0, K; };  // row0, K: the leaf's folded row list in DeviceModel::fold_row
+struct ItemGeom { int32_t leaf, qbeg, nq, dc0, n_dc, row0, K, lowK; };  // row0, K: the leaf's folded row list in DeviceModel::fold_row; lowK: rows per stage (!ONE)
 // item -> (chunk group, tile) -> leaf and query range; identical arithmetic in the producer and in every consumer warp
 __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, int64_t n_tiles, int32_t L, int32_t n_dchunks, int dg, const int32_t *__restrict__ offset,
                                                   const int32_t *__restrict__ tile_off, const int32_t *__restrict__ fold_off, const int32_t *__restrict__ tile_leaf)
@@ -68,6 +72,7 @@ __device__ __forceinline__ ItemGeom item_geometry(int64_t item, int64_t tile0, i
 	g.n_dc = min(dg, n_dchunks - g.dc0);
 	g.row0 = __ldg(fold_off + lo);
 	g.K = __ldg(fold_off + lo + 1) - g.row0;
+	g.lowK = MM_K;
 	return g;
 }
 } // namespace
@@ -87,13 +92,13 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	constexpr int LOWD = NT < (CUBIC ? 2 : 4) ? NT : (CUBIC ? 2 : 4);
 	constexpr int LOWK = 1 << (LOGF * LOWD);
 	constexpr int MM_NS = ONE ? MM_NS_ONE : MM_NS_MULTI;
-	constexpr int MM_NW = ONE ? 2 : MM_NS;  // weight buffers: per item (ONE) or per stage
+	constexpr int MM_NW = 2;  // weight buffers: per item (all rows of a chunk when ONE, the low-dimension products otherwise)
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *sV = reinterpret_cast<double *>(smem_raw);             // [MM_NS][MM_K][MM_LDV]
 	double *sW = sV + MM_NS * MM_K * MM_LDV;                       // [MM_NW][MM_K][MM_LDW]
 	double *sF = sW + MM_NW * MM_K * MM_LDW;                       // [NT*F][MM_Q]   producer only
-	double *sL = sF + NT * F * MM_Q;                               // [LOWK][MM_Q]   producer only
-	int32_t *sQi = reinterpret_cast<int32_t *>(sL + LOWK * MM_Q);  // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
+	double *sH = sF + NT * F * MM_Q;                               // [MM_NS][MM_Q]  the stage's high factor of every query (!ONE)
+	int32_t *sQi = reinterpret_cast<int32_t *>(sH + MM_NS * MM_Q); // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
 	double *sStage = reinterpret_cast<double *>(sQi + 2 * MM_Q);   // [MM_CONSUMERS][8][MM_STG_LD]  (ONE only) results on their way to TMA bulk stores
 	__shared__ __align__(8) uint64_t full_bar[MM_NS], empty_bar[MM_NS], item_bar[2];
 	__shared__ ItemGeom s_item[2];  // the producers locate the item's leaf (a binary search over tile offsets); the consumers read it here
@@ -154,93 +159,74 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 #pragma unroll
 				for (int c = 0; c < F; c++) sF[(d * F + c) * MM_Q + q] = q < ig.nq ? gsum[c] : 0.0;
 			}
-			// ---- products over the low dimensions (mixed radix nd[0..LOWD)): sL[kl][q], kl < lowK <= 16
+			// ---- products over the low dimensions (mixed radix nd[0..LOWD)): W[kl][q], kl < lowK <= 16, written ONCE per item into
+			//      the item's weight buffer (rows lowK .. MM_K-1 are zero: stages are padded to whole MMA k-steps)
 			int lowK = 1;
 #pragma unroll
 			for (int d = 0; d < LOWD; d++) lowK *= nd[d];
 			{
+				double *W_ = sW + (size_t)ib * MM_K * MM_LDW + q;
 				int dig[LOWD];
 #pragma unroll
 				for (int d = 0; d < LOWD; d++) dig[d] = 0;
-				for (int kl = 0; kl < lowK; kl++) {
-					double w = 1.0;
+				for (int kl = 0; kl < MM_K; kl++) {
+					double w = 0.0;
+					if (kl < lowK) {
+						w = 1.0;
 #pragma unroll
-					for (int d = 0; d < LOWD; d++) w *= sF[(d * F + dig[d]) * MM_Q + q];
-					sL[kl * MM_Q + q] = w;
+						for (int d = 0; d < LOWD; d++) w *= sF[(d * F + dig[d]) * MM_Q + q];
 #pragma unroll
-					for (int d = 0; d < LOWD; d++) {  // increment the mixed-radix counter
-						if (++dig[d] < nd[d]) break;
-						dig[d] = 0;
+						for (int d = 0; d < LOWD; d++) {  // increment the mixed-radix counter
+							if (++dig[d] < nd[d]) break;
+							dig[d] = 0;
+						}
 					}
+					W_[kl * MM_LDW] = w;
 				}
 			}
 			const int32_t K = ig.K;
-			const int n_stages = (K + MM_K - 1) / MM_K;
+			// ONE: all K <= 16 rows are one stage.  Otherwise a stage is one run of lowK rows sharing their high digits.
+			const int rows_per_stage = ONE ? MM_K : lowK;
+			const int n_stages = ONE ? 1 : K / lowK;
+			if (pw == 0 && lane == 0) s_item[ib].lowK = rows_per_stage;
 			const int32_t *rows = m.fold_row + ig.row0;
 			const int n_steps = ig.n_dc * n_stages;
 			// everything a step needs that does not depend on the stage being free is prepared BEFORE waiting for it:
 			// the row index of this lane's TMA copy (a global load) and the 16 weights (kept in registers).
 			// Rows are padded to a multiple of 4 per stage with zero weights (the MMA consumes 4 rows at a time); the
 			// padding lanes copy the leaf's last row so that 0 * value stays finite.
+			const int kc_all = ONE ? min(MM_K, K) : lowK;
+			const int kc4 = (kc_all + 3) & ~3;
 			auto row_of = [&](int c, int ln) -> int32_t {
-				const int kc4 = (min(MM_K, K - c * MM_K) + 3) & ~3;
-				return ln < kc4 ? __ldg(rows + min(c * MM_K + ln, K - 1)) : 0;
+				return ln < kc4 ? __ldg(rows + min(c * rows_per_stage + min(ln, kc_all - 1), K - 1)) : 0;
 			};
 			int32_t my_row = row_of(0, lane);
-			int low = 0, hd[NT > LOWD ? NT - LOWD : 1];
+			int hd[NT > LOWD ? NT - LOWD : 1];
 			double ph = 1.0;
-			if (ONE) {
-				// all rows fit one stage: the weights do not depend on the chunk, write them once per item (item buffer ib;
-				// the first stage barrier of the item publishes them)
-				double *W_ = sW + (size_t)ib * MM_K * MM_LDW + q;
-#pragma unroll
-				for (int kk = 0; kk < MM_K; kk++) W_[kk * MM_LDW] = kk < K ? sL[kk * MM_Q + q] : 0.0;
-			}
 			for (int s = 0; s < n_steps; s++, g++) {
 				const int dc = s / n_stages, c = s - dc * n_stages;
 				const int st = g % MM_NS;
-				const int kc = min(MM_K, K - c * MM_K), kc4 = (kc + 3) & ~3;
-				// ---- weights of the stage: w[kk] = low[k % lowK] * high(k / lowK), k = c*MM_K + kk, walked incrementally
-				double wreg[ONE ? 1 : MM_K];
 				if (!ONE) {
-					// the mixed-radix position (low, hd[]) of row k is carried from stage to stage (no divisions): a chunk
-					// starts at row 0, and every full stage advances it by exactly MM_K rows
-					auto high_product = [&]() {
-						double p = 1.0;
-#pragma unroll
-						for (int d = LOWD; d < NT; d++) p *= sF[(d * F + hd[d - LOWD]) * MM_Q + q];
-						return p;
-					};
+					// the stage's high factor: mixed-radix digits of stage c over the high dimensions, carried from stage to stage
 					if (c == 0) {
-						low = 0;
 #pragma unroll
 						for (int d = LOWD; d < NT; d++) hd[d - LOWD] = 0;
-						ph = high_product();
-					}
+					} else {
 #pragma unroll
-					for (int kk = 0; kk < MM_K; kk++) {
-						wreg[kk] = kk < kc ? sL[low * MM_Q + q] * ph : 0.0;
-						if (++low == lowK) {
-							low = 0;
-#pragma unroll
-							for (int d = LOWD; d < NT; d++) {
-								if (++hd[d - LOWD] < nd[d]) break;
-								hd[d - LOWD] = 0;
-							}
-							ph = high_product();
+						for (int d = LOWD; d < NT; d++) {
+							if (++hd[d - LOWD] < nd[d]) break;
+							hd[d - LOWD] = 0;
 						}
 					}
+					ph = 1.0;
+#pragma unroll
+					for (int d = LOWD; d < NT; d++) ph *= sF[(d * F + hd[d - LOWD]) * MM_Q + q];
 				}
 				const int32_t row = my_row;
 				if (pw == 0 && s + 1 < n_steps) my_row = row_of((c + 1 == n_stages) ? 0 : c + 1, lane);  // row index of the NEXT step's copy
 				mbar_wait(&empty_bar[st], ((g / MM_NS) & 1u) ^ 1u);
-				if (!ONE) {
-					double *W_ = sW + (size_t)st * MM_K * MM_LDW + q;
-#pragma unroll
-					for (int kk = 0; kk < MM_K; kk++)
-						if (kk < kc4) W_[kk * MM_LDW] = wreg[kk];
-				}
-				__syncwarp();  // every lane's weights are written before lane 0 arrives on the stage barrier
+				if (!ONE) sH[st * MM_Q + q] = ph;
+				__syncwarp();  // every lane's factor is written before lane 0 arrives on the stage barrier
 				if (pw == 0) {
 					// ---- the stage's value rows: one TMA bulk copy per row segment
 					const int32_t d0 = (ig.dc0 + dc) * MM_D;
@@ -270,7 +256,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 		mbar_wait(&full_bar[g % MM_NS], (g / MM_NS) & 1u);
 		const ItemGeom ig = s_item[ib];
 		const int32_t K = ig.K;
-		const int n_stages = (K + MM_K - 1) / MM_K;
+		const int n_stages = ONE ? 1 : K / ig.lowK;
 		const int n_steps = ig.n_dc * n_stages;
 		const int n_mi = min(4, (ig.nq - wq * 32 + 7) >> 3);  // 8-query blocks beyond the tile's last query hold only padding
 		for (int s = 0; s < n_steps; s++, g++) {
@@ -283,15 +269,21 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 					for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 			}
 			mbar_wait(&full_bar[st], (g / MM_NS) & 1u);
-			const int kc = (min(MM_K, K - c * MM_K) + 3) & ~3;  // padded to whole MMA k-steps with zero weights
-			const double *w_base = sW + (size_t)(ONE ? ib : st) * MM_K * MM_LDW + wq * 32 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr]
+			const int kc = ((ONE ? min(MM_K, K) : ig.lowK) + 3) & ~3;  // padded to whole MMA k-steps with zero weights
+			const double *w_base = sW + (size_t)ib * MM_K * MM_LDW + wq * 32 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr]
 			const double *v_base = sV + (size_t)st * MM_K * MM_LDV + wd * 32 + fr;  // B[fc][fr] = V[k0 + fc][d0 + fr]
 			if (n_mi > 0) {
+				double hq[4];  // the stage's high factor of this lane's four fragment rows (queries)
+#pragma unroll
+				for (int mi = 0; mi < 4; mi++) hq[mi] = ONE ? 1.0 : sH[st * MM_Q + wq * 32 + mi * 8 + fr];
 #pragma unroll 2
 				for (int k0 = 0; k0 < kc; k0 += 4) {
 					double a[4], bf[4];
 #pragma unroll
-					for (int mi = 0; mi < 4; mi++) a[mi] = w_base[(k0 + fc) * MM_LDW + mi * 8];
+					for (int mi = 0; mi < 4; mi++) {
+						a[mi] = w_base[(k0 + fc) * MM_LDW + mi * 8];
+						if (!ONE) a[mi] *= hq[mi];  // w = low * high: the product the reference's weight is
+					}
 #pragma unroll
 					for (int ni = 0; ni < 4; ni++) bf[ni] = v_base[(k0 + fc) * MM_LDV + ni * 8];
 #pragma unroll
@@ -378,8 +370,9 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 namespace {
 size_t mma_smem_bytes(int N, int F, int lowk, bool one)
 {
-	const int ns = one ? MM_NS_ONE : MM_NS_MULTI, nw = one ? 2 : MM_NS_MULTI;
-	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + lowk * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64 +
+	const int ns = one ? MM_NS_ONE : MM_NS_MULTI, nw = 2;
+	(void)lowk;
+	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + ns * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64 +
 	       ((one && MM_TMA_STORE) ? (size_t)MM_CONSUMERS * 8 * MM_STG_LD * sizeof(double) : 0);
 }
 template <int NT, bool CUBIC, bool EXACT, bool ONE>
