@@ -281,6 +281,11 @@ int loco_peer_copy_async(void *dst, const void *src, size_t bytes, void *cuda_st
  *          "leaf_poly" 1 (default): scalar functions on tensor-product leaves that lie inside one polynomial piece of every basis function
  *                 (every bootstrap grid) evaluate the leaf's single tensor-product polynomial by nested Horner (changes the
  *                 summation order, within the 1e-12 bar) | 0: N*F basis polynomials + sum-factorised contraction;
+ *          "fast_scatter" 1 (default): path 5's scatter kernel specialised for models with power-of-two domain widths, a uniform dyadic
+ *                 locate grid and split-plane-consistent leaf boxes (every bootstrap grid); same arithmetic | 0: the general kernel;
+ *          "bulk_eval" 1: the evaluation kernel of path 5 works on items of up to 96 records of one leaf that the TMA engine
+ *                 prefetches into shared memory an item ahead (cp.async.bulk + mbarrier) | 0 (default; measured equal): per-lane record loads one group ahead;
+ *          "aggregate" 1 (default): the sort kernels of paths 4 / 5 issue one slot atomic per group of lanes of a warp that share a leaf | 0: one per query;
  *          "adaptive" 1 (default): with "path" 0 big scalar batches on tensor-product leaves take the leaf buckets (path 5) while the batches
  *                 seen so far fit the buckets' uniform-batch capacity, and the exact counting sort (path 4) once more than 4 % of the queries
  *                 overflow (skewed batches); decided from counters the kernels keep, without synchronisation | 0: always the buckets;

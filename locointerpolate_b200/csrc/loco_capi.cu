@@ -82,7 +82,7 @@ struct loco_model {
 	int64_t device_bytes = 0;
 	mutable std::string err = "no error";
 	int64_t launches = 0;
-	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1, opt_fused_errgen = 1, opt_leaf_poly = 1, opt_adaptive = 1;
+	int64_t opt_path = 0, opt_fp32 = 0, opt_lut = 1, opt_chunk = 0, opt_mesh_simt = 0, opt_overlap = 3, opt_uniform = 1, opt_fused_errgen = 1, opt_leaf_poly = 1, opt_adaptive = 1, opt_aggregate = 1, opt_bulk_eval = 0, opt_fast_scatter = 1;
 	const uint32_t *d_lut = nullptr;  // kept so that the "lut" option can switch the locate grid off and on
 	Workspace ws[kSlots];
 	// auxiliary streams: consecutive chunks of the sorted path run round-robin on them so that the latency-bound sort
@@ -305,6 +305,18 @@ int build_device_model(loco_model *m)
 	CUDA_OK(m, cudaMemset(m->d_term_wv, 0, (size_t)(m->n_terms + 2) * sizeof(double)));
 	dm.term_wv = m->d_term_wv;
 	CUDA_OK(m, cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
+	if (f.D > 1 && getenv("LOCO_L2_PERSIST_MB")) {
+		// EXPERIMENT switch (off by default).  The mesh tile kernels re-read the slice of the value table all CTAs share (TMA
+		// copies with an L2::evict_last policy) while the result stream passes through the same L2, and 69-75 % of those
+		// re-reads miss (ncu r02h).  A persisting-L2 set-aside for the evict_last lines was measured and made it WORSE
+		// (c3: 17.7 ms without, 18.5 ms with 48 MB, 29.6 ms with 96 MB; c4b unchanged): the carve-out is taken from the
+		// capacity that buffers the dirty result lines.  See profiles/README.md.
+		int max_persist = 0;
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, m->device);
+		const size_t want = (size_t)atoi(getenv("LOCO_L2_PERSIST_MB")) << 20;
+		if (max_persist > 0 && want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)max_persist, want));
+		cudaGetLastError();
+	}
 	// tensor-product leaf blocks
 	dm.tensor_F = 0;
 	if (f.tensor_F > 0 && f.N <= kMaxTemplateN) {
@@ -482,6 +494,9 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 				if ((rc = grow(m, buf, have, bucket_work_bytes(dm, chunk)))) return rc;
 				bw[k] = carve_bucket_work(dm, chunk, *buf);
 				if (m->opt_path == 0 && deriv_dir < 0) bw[k].stats = m->d_stats + k;
+				bw[k].aggregate = m->opt_aggregate != 0;
+				bw[k].bulk = m->opt_bulk_eval != 0;
+				bw[k].fast = m->opt_fast_scatter != 0;
 			}
 			if (ns > 1) {
 				CUDA_OK(m, cudaEventRecord(m->ev_fork, st));
@@ -513,6 +528,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 				if ((rc = grow(m, &w.sortedx[k - 1], &w.sortedx_b[k - 1], sorted_work_bytes(dm, chunk)))) return rc;
 				sw[k] = carve_sorted_work(dm, w.sortedx[k - 1]);
 			}
+			for (int k = 0; k < ns; k++) sw[k].aggregate = m->opt_aggregate != 0;
 			if (m->opt_path == 0 && deriv_dir < 0 && m->d_stats && bucket_path_supported(dm) && !dm.ecell_off) {
 				// the counting sort reports what the fixed-capacity buckets WOULD have overflowed, so that a stream of batches that
 				// turns uniform again goes back to them
@@ -1381,6 +1397,9 @@ int loco_set_option(loco_model_t *m, const char *name, int64_t value)
 		m->dm.tl_poly = (value && m->dm.tp_stride > 0) ? m->d_tl_poly : nullptr;
 		return LOCO_OK;
 	}
+	if (!strcmp(name, "fast_scatter")) { m->opt_fast_scatter = value; return LOCO_OK; }  // 1 (default): scatter kernel specialised for uniform locate grids / power-of-two domains
+	if (!strcmp(name, "bulk_eval")) { m->opt_bulk_eval = value; return LOCO_OK; }  // 1: bucket evaluation from TMA-prefetched work items, 0 (default): register prefetch one group ahead
+	if (!strcmp(name, "aggregate")) { m->opt_aggregate = value; return LOCO_OK; }  // 0: one slot atomic per query, 1 (default): one per run of equal leaves in a warp
 	if (!strcmp(name, "adaptive")) { m->opt_adaptive = value; if (!value) m->skewed = false; return LOCO_OK; }  // 0: path 0 never leaves the leaf buckets
 	if (!strcmp(name, "fused_errgen")) { m->opt_fused_errgen = value; return LOCO_OK; }  // 0: the three-kernel form of loco_error_check_generated_device
 	if (!strcmp(name, "ecell_poly")) {  // 1: polynomial form of the evaluation cells no knot crosses (see loco_cellpoly.h), 0: term lists

@@ -202,6 +202,7 @@ int launch_eval_scalar_tiles(const DeviceModel &m, const double *q, int64_t Q, d
 struct SkewStats { long long overflow, total; };
 
 struct SortedWork {
+	bool aggregate;    // warp-aggregated histogram / cursor atomics (option "aggregate")
 	SkewStats *stats;  // may be null
 	int32_t stats_cap; // bucket capacity the overflow is counted against
 	int32_t *count;    // [L] histogram (zero between chunks)
@@ -218,6 +219,9 @@ int launch_eval_scalar_sorted_chunk(const DeviceModel &m, const double *q, int64
 // ---- single-pass fixed-capacity leaf buckets (loco_bucket.cu)
 struct BucketWork {
 	SkewStats *stats;  // may be null
+	bool aggregate;    // warp-aggregated slot atomics (option "aggregate")
+	bool bulk;         // evaluation with TMA-prefetched work items (option "bulk_eval")
+	bool fast;         // specialised scatter kernel where the model allows it (option "fast_scatter")
 	int32_t *count;    // [L] queries that asked for a slot in the leaf's bucket (zero between chunks)
 	int32_t *n_ovf;    // number of overflow entries
 	int32_t *ovf;      // [chunk] query indices whose bucket was full

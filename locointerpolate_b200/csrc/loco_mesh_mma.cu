@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
                                                                          const int32_t *__restrict__ tile_off, const int32_t *__restrict__ tile_leaf,
                                                                          double *__restrict__ out,
                                                                          int64_t out_stride, int32_t n_dchunks, int32_t dg, int64_t tile0, int64_t n_tiles_arg,
-                                                                         int64_t ring_base)
+                                                                         int64_t ring_base, int dbg)
 {
 	constexpr int F = CUBIC ? 4 : 2;
 	constexpr int LOGF = CUBIC ? 2 : 1;
@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 					if (lane == 0) mbar_expect_tx(&full_bar[st], row_bytes * (uint32_t)kc4);
 					__syncwarp();
 					if (lane < kc4)
-						tma_bulk_g2s_hint(sV + ((size_t)st * MM_K + lane) * MM_LDV, m.values + (int64_t)row * m.value_stride + d0, row_bytes, &full_bar[st], keep);
+					{
+						if (dbg & 1) tma_bulk_g2s(sV + ((size_t)st * MM_K + lane) * MM_LDV, m.values + (int64_t)row * m.value_stride + d0, row_bytes, &full_bar[st]);  // EXPERIMENT: no L2 hint
+						else tma_bulk_g2s_hint(sV + ((size_t)st * MM_K + lane) * MM_LDV, m.values + (int64_t)row * m.value_stride + d0, row_bytes, &full_bar[st], keep);
+					}
 				} else if (lane == 0) {
 					mbar_arrive(&full_bar[st]);
 				}
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	const int fr = lane >> 2, fc = lane & 3;   // fragment coordinates: A[fr][fc], B[fc][fr], C[fr][2*fc .. 2*fc+1]
 	const bool vec_out = ((out_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 	const bool wide_out = ((out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);  // rows 32-byte aligned
+	const uint64_t wr_policy = l2_policy_evict_first();
 	uint32_t g = 0, it = 0;
 	double acc[4][4][2];  // [query block mi][component block ni][2]
 	for (int64_t item = blockIdx.x; item < total; item += gridDim.x, it++) {
@@ -337,8 +341,14 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 							const double s0 = odd ? acc[mi][n0][0] : acc[mi][n1][0], s1 = odd ? acc[mi][n0][1] : acc[mi][n1][1];
 							const double r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
 							if (qi < 0) continue;
-							if (odd) st_stream_f64x4(o + n1 * 8 + 2 * (fc - 1), r0, r1, acc[mi][n1][0], acc[mi][n1][1]);
-							else st_stream_f64x4(o + n0 * 8 + 2 * fc, acc[mi][n0][0], acc[mi][n0][1], r0, r1);
+							// 256-bit stores with an explicit L2 evict_first POLICY (st.global.L2::cache_hint): measured 5 % faster on c3 than
+							// the .cs qualifier (17.9 -> 17.0 ms; plain write-back 17.2, evict_unchanged 17.4; LOCO_MESH_DBG 8 / 2 / 6 select them)
+							double *po = odd ? o + n1 * 8 + 2 * (fc - 1) : o + n0 * 8 + 2 * fc;
+							const double v0 = odd ? r0 : acc[mi][n0][0], v1 = odd ? r1 : acc[mi][n0][1], v2 = odd ? acc[mi][n1][0] : r0, v3 = odd ? acc[mi][n1][1] : r1;
+							if ((dbg & 14) == 0) st_policy_f64x4(po, v0, v1, v2, v3, wr_policy);
+							else if (dbg & 8) st_stream_f64x4(po, v0, v1, v2, v3);
+							else if ((dbg & 6) == 2) st_plain_f64x4(po, v0, v1, v2, v3);
+							else st_policy_f64x4(po, v0, v1, v2, v3, l2_policy_no_allocate());
 						}
 					}
 				} else {
@@ -384,7 +394,10 @@ void run_mma1(const DeviceModel &m, const SortWork &w, double *out, int64_t out_
 	const size_t smem = mma_smem_bytes(NT, CUBIC ? 4 : 2, 1 << ((CUBIC ? 2 : 1) * LOWD), ONE);
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	LOCO_KERNEL("mesh_tensor_mma", st);
-	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, w.tile_leaf, out, out_stride, n_dchunks, dg, tile0, n_tiles, ring_base);
+	static const int dbg = getenv("LOCO_MESH_DBG") ? atoi(getenv("LOCO_MESH_DBG")) : 0;  // measurement experiments only
+	static const int grid_env = getenv("LOCO_MESH_GRID") ? atoi(getenv("LOCO_MESH_GRID")) : 0;
+	if (grid_env > 0) grid = grid_env;
+	kern<<<grid, MM_THREADS, smem, st>>>(m, w.xs, w.offset, w.tile_off, w.tile_leaf, out, out_stride, n_dchunks, dg, tile0, n_tiles, ring_base, dbg);
 }
 template <int NT, bool CUBIC, bool EXACT>
 void run_mma(const DeviceModel &m, const SortWork &w, double *out, int64_t out_stride, int n_dchunks, int dg, int grid, int64_t tile0, int64_t n_tiles,
@@ -412,9 +425,14 @@ int launch_mesh_tensor_mma(const DeviceModel &m, const SortWork &w, int64_t Q, d
 	// chunks per item: enough steps per item to amortise the per-item tables, while the slice of the value table all
 	// CTAs share at a time (rows x dg*128 components) stays well inside the L2
 	const int n_stages = (m.tensor_K + MM_K - 1) / MM_K;
-	int dg = std::max(4, (32 + n_stages - 1) / n_stages);
-	const int64_t slice_cap = ((int64_t)28 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
-	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)dg, std::max<int64_t>(slice_cap, 4), (int64_t)n_dchunks}));
+	// >= 32 steps per item where the slice allows it (items with few stages need several chunks to amortise their tables),
+	// a slice of at most ~24 MB (ncu r02h: the 62 MB slice of the 6-D cubic table missed the L2 on 75 % of its re-reads)
+	static const int dg_env = getenv("LOCO_MESH_DG") ? atoi(getenv("LOCO_MESH_DG")) : 0;  // measurement experiments
+	int dg = std::max(1, (32 + n_stages - 1) / n_stages);
+	const int64_t slice_cap = ((int64_t)24 << 20) / std::max<int64_t>(1, m.R * MM_D * 8);
+	dg = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::max(dg, 4), std::max<int64_t>(slice_cap, 1), (int64_t)n_dchunks}));
+	if (n_stages < 8) dg = std::max(dg, std::min(4, n_dchunks));  // one-stage chunks: never fewer than 4 chunks per item
+	if (dg_env > 0) dg = std::min(dg_env, n_dchunks);
 	const int grid = sm_count * 2;
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_MCASE(NT)                                                                                                  \

@@ -70,7 +70,8 @@ __device__ __forceinline__ int32_t eval_cell(const DeviceModel &m, const Coord<N
 // 1. locate + histogram
 // ---------------------------------------------------------------------------------------------------
 constexpr int kCountItems = 2;  // queries per thread: two independent load -> locate -> atomic chains in flight
-template <int NT>
+// AGG: lanes of a warp with the same sort key share one atomic (see bucket_scatter_kernel)
+template <int NT, bool AGG>
 __global__ void __launch_bounds__(256) sorted_count_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, int32_t *__restrict__ leaf_out,
                                                             uint8_t *__restrict__ status_out, double *__restrict__ out, int32_t *count)
 {
@@ -88,15 +89,23 @@ __global__ void __launch_bounds__(256) sorted_count_kernel(DeviceModel m, const 
 #pragma unroll
 	for (int k = 0; k < kCountItems; k++) {
 		const int64_t i = i0 + k * 256;
-		if (i >= Q) continue;
-		Coord<NT> x;
-		map_to_cube<NT>(m, p[k], x);
-		const int32_t leaf = descend<NT>(m, x);
-		const uint8_t st = located_status<NT>(m, x, leaf);
-		leaf_out[i] = leaf;
-		status_out[i] = st;
-		if (st == ST_OK) atomicAdd(count + eval_cell<NT>(m, x, leaf), 1);  // result unused: a fire-and-forget RED
-		else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+		int32_t key = -1 - (int)(threadIdx.x & 31);  // lanes without a valid query match nobody
+		if (i < Q) {
+			Coord<NT> x;
+			map_to_cube<NT>(m, p[k], x);
+			const int32_t leaf = descend<NT>(m, x);
+			const uint8_t st = located_status<NT>(m, x, leaf);
+			leaf_out[i] = leaf;
+			status_out[i] = st;
+			if (st == ST_OK) key = eval_cell<NT>(m, x, leaf);
+			else out[i] = __longlong_as_double(0x7ff8000000000000LL);
+		}
+		if constexpr (AGG) {
+			const unsigned peers = __match_any_sync(0xffffffffu, key);
+			if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(count + key, __popc(peers));
+		} else {
+			if (key >= 0) atomicAdd(count + key, 1);  // result unused: a fire-and-forget RED
+		}
 	}
 }
 
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(kScanThreads) sorted_scan_kernel(int32_t *coun
 // 2. scatter into leaf buckets
 // ---------------------------------------------------------------------------------------------------
 constexpr int kScatterItems = 2;  // queries per thread: two independent load -> atomic -> store chains in flight
-template <int NT>
+template <int NT, bool AGG>
 __global__ void __launch_bounds__(256) sorted_scatter_kernel(DeviceModel m, const double *__restrict__ q, int64_t Q, const int32_t *__restrict__ leaf_in,
                                                               const uint8_t *__restrict__ status_in, int32_t *cursor, double *__restrict__ xs)
 {
@@ -202,8 +211,20 @@ __global__ void __launch_bounds__(256) sorted_scatter_kernel(DeviceModel m, cons
 			}
 	}
 #pragma unroll
-	for (int k = 0; k < kScatterItems; k++)
-		if (st[k] == ST_OK) pos[k] = atomicAdd(cursor + leaf[k], 1);
+	for (int k = 0; k < kScatterItems; k++) {
+		if constexpr (AGG) {
+			const int lane_id = threadIdx.x & 31;
+			const int32_t key = st[k] == ST_OK ? leaf[k] : -1 - lane_id;
+			const unsigned peers = __match_any_sync(0xffffffffu, key);
+			const int leader = __ffs(peers) - 1;
+			int base = 0;
+			if (st[k] == ST_OK && lane_id == leader) base = atomicAdd(cursor + leaf[k], __popc(peers));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			pos[k] = base + __popc(peers & ((1u << lane_id) - 1));
+		} else {
+			if (st[k] == ST_OK) pos[k] = atomicAdd(cursor + leaf[k], 1);
+		}
+	}
 #pragma unroll
 	for (int k = 0; k < kScatterItems; k++) {
 		if (st[k] != ST_OK) continue;
@@ -327,7 +348,9 @@ template <int NT>
 void run_count(const DeviceModel &m, const double *q, int64_t Q, int32_t *leaf, uint8_t *status, double *out, const SortedWork &w, cudaStream_t st)
 {
 	{ LOCO_KERNEL("sorted_count", st);
-	sorted_count_kernel<NT><<<(unsigned)((Q + 256 * kCountItems - 1) / (256 * kCountItems)), 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
+	const unsigned g = (unsigned)((Q + 256 * kCountItems - 1) / (256 * kCountItems));
+	if (w.aggregate) sorted_count_kernel<NT, true><<<g, 256, 0, st>>>(m, q, Q, leaf, status, out, w.count);
+	else sorted_count_kernel<NT, false><<<g, 256, 0, st>>>(m, q, Q, leaf, status, out, w.count); }
 	LOCO_KERNEL("sorted_scan", st);
 	sorted_scan_kernel<<<1, kScanThreads, (kScanSeg + kScanSeg / 32) * sizeof(int), st>>>(w.count, w.cursor, sort_buckets(m), w.stats, w.stats_cap);
 }
@@ -335,7 +358,9 @@ template <int NT>
 void run_scatter(const DeviceModel &m, const double *q, int64_t Q, const int32_t *leaf, const uint8_t *status, const SortedWork &w, cudaStream_t st)
 {
 	LOCO_KERNEL("sorted_scatter", st);
-	sorted_scatter_kernel<NT><<<(unsigned)((Q + 256 * kScatterItems - 1) / (256 * kScatterItems)), 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
+	const unsigned g = (unsigned)((Q + 256 * kScatterItems - 1) / (256 * kScatterItems));
+	if (w.aggregate) sorted_scatter_kernel<NT, true><<<g, 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
+	else sorted_scatter_kernel<NT, false><<<g, 256, 0, st>>>(m, q, Q, leaf, status, w.cursor, w.xs);
 }
 template <int NT, bool CUBIC, bool EXACT>
 void run_eval(const DeviceModel &m, int64_t Q, const SortedWork &w, double *out, int sm_count, bool fp32, int deriv_dir, cudaStream_t st)
@@ -363,7 +388,7 @@ size_t sorted_work_bytes(const DeviceModel &m, int64_t chunk)
 SortedWork carve_sorted_work(const DeviceModel &m, void *base)
 {
 	SortedWork w;
-	w.stats = nullptr; w.stats_cap = 0x7fffffff;
+	w.stats = nullptr; w.stats_cap = 0x7fffffff; w.aggregate = true;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
 	w.count = p; p += sort_buckets(m);
 	w.cursor = p; p += sort_buckets(m) + 1;

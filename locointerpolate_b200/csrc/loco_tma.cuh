@@ -63,6 +63,21 @@ __device__ __forceinline__ void st_stream_f64x4(double *p, double a, double b, d
 {
 	asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
+// 256-bit store variants for cache-policy experiments: default write-back, and with an explicit L2 policy
+__device__ __forceinline__ void st_plain_f64x4(double *p, double a, double b, double c, double d)
+{
+	asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void st_policy_f64x4(double *p, double a, double b, double c, double d, uint64_t policy)
+{
+	asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_no_allocate()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
 // shared -> global bulk copy executed by the TMA engine (bulk async-group completion); size and both addresses multiples of 16 B
 __device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {

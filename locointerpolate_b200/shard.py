@@ -121,6 +121,12 @@ class ShardedModel:
 # ------------------------------------------------------------------------------------------------------------------
 # Streaming exchange for scalar results: batch b (one shard per rank) is consumed on rank b % world
 # ------------------------------------------------------------------------------------------------------------------
+# measurement switches (bench experiments only: they break the exchange's guarantees)
+import os as _os
+_EXPERIMENT_NO_COPY = bool(_os.environ.get("LOCO_EX_NOCOPY"))
+_EXPERIMENT_NO_SIGNAL = bool(_os.environ.get("LOCO_EX_NOSIGNAL"))
+
+
 class _ArrayView:
     """CUDA array interface over a raw device pointer (a peer-mappable buffer from the C ABI), for torch.as_tensor"""
 
@@ -269,7 +275,8 @@ class RotatingExchange:
                     if self.time_copies:
                         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         t0.record()
-                    capi.peer_copy_async(dst, self.local[k].data_ptr(), self.n * self.itemsize, self.copy_stream.cuda_stream)
+                    if not _EXPERIMENT_NO_COPY:
+                        capi.peer_copy_async(dst, self.local[k].data_ptr(), self.n * self.itemsize, self.copy_stream.cuda_stream)
                     if t0 is not None:
                         t1.record()
                         self.copy_events.append((t0, t1, self.n * self.itemsize))
@@ -303,7 +310,7 @@ class RotatingExchange:
             return
         if self.cuda:
             with torch.cuda.stream(self.copy_stream):
-                if self.transport == "ipc":
+                if self.transport == "ipc" and not _EXPERIMENT_NO_SIGNAL:
                     dist.all_reduce(self._sig, group=self.group)   # stream-ordered: passes when every rank's copies of step s landed
                 ev = torch.cuda.Event()
                 ev.record()
