@@ -290,8 +290,8 @@ int loco_peer_copy_async(void *dst, const void *src, size_t bytes, void *cuda_st
  *                 seen so far fit the buckets' uniform-batch capacity, and the exact counting sort (path 4) once more than 4 % of the queries
  *                 overflow (skewed batches); decided from counters the kernels keep, without synchronisation | 0: always the buckets;
  *          "fused_errgen" 1 (default): loco_error_check_generated_device as one fused kernel where supported | 0: generate / evaluate / reduce kernels;
- *          "ecell_poly" 1: evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
- *                 (changes the summation order, within the 1e-12 bar) | 0 (default in this round): always the term list */
+ *          "ecell_poly" 1 (default): evaluation cells that no knot crosses are evaluated from their single tensor-product polynomial
+ *                 (changes the summation order, within the 1e-12 bar) | 0: always the term list */
 int loco_set_option(loco_model_t *m, const char *name, int64_t value);
 /* kernels launched by this handle since creation (for bench accounting) */
 int64_t loco_kernel_launches(const loco_model_t *m);

@@ -36,7 +36,34 @@ __device__ __forceinline__ void ld_sector_cg(const double *p, double &a, double 
 	asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+// Every leaf's slot counter sits in its own 128-byte line: the L2 serialises atomics per LINE, and a skewed batch (half of
+// the queries in 1 % of the leaves) sends millions of them to the few lines that would hold 32 neighbouring counters each.
+constexpr int kCountStride = 32;
 constexpr int kItems = 4;  // queries per thread in the scatter pass: independent load -> locate -> atomic -> store chains in flight
+
+// Overflow list (queries whose bucket was full): ONE list-counter atomic per warp for ALL items of its threads -- a skewed
+// batch sends half of every warp here, and an append per item (a dependent atomic round trip each) made the scatter pass
+// 2.6 x slower on such a batch.  Called by the whole warp, outside divergent code.
+template <int ITEMS>
+__device__ __forceinline__ void append_overflow(int n_over, const bool (&live)[ITEMS], const int32_t (&slot)[ITEMS], int32_t cap, int64_t i0,
+                                                int32_t *__restrict__ ovf, int32_t *n_ovf)
+{
+	if (!__any_sync(0xffffffffu, n_over > 0)) return;
+	const int lane_id = threadIdx.x & 31;
+	int incl = n_over;  // inclusive warp prefix sum of the per-thread counts
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const int v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane_id >= off) incl += v;
+	}
+	const int total = __shfl_sync(0xffffffffu, incl, 31);
+	int base = 0;
+	if (lane_id == 0) base = atomicAdd(n_ovf, total);
+	base = __shfl_sync(0xffffffffu, base, 0) + incl - n_over;
+#pragma unroll
+	for (int k = 0; k < ITEMS; k++)
+		if (live[k] && slot[k] >= cap) ovf[base++] = (int32_t)(i0 + k * 256);
+}
 
 // AGG: lanes of a warp that ask for a slot in the SAME leaf's bucket share one atomicAdd (structured batches -- lattice
 // sweeps, trajectories -- put runs of consecutive queries into one leaf; their same-address atomics would serialise in the L2)
@@ -92,13 +119,14 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 			int base = 0;
 			if (dbg & 2) base = (int)((blockIdx.x * 7 + k) % 100);  // EXPERIMENT: no atomic
 			else
-			if (live[k] && lane_id == leader) base = atomicAdd(count + leaf[k], __popc(peers));
+			if (live[k] && lane_id == leader) base = atomicAdd(count + (int64_t)leaf[k] * kCountStride, __popc(peers));
 			base = __shfl_sync(0xffffffffu, base, leader);
 			slot[k] = base + __popc(peers & ((1u << lane_id) - 1));
 		} else {
-			if (live[k]) slot[k] = atomicAdd(count + leaf[k], 1);
+			if (live[k]) slot[k] = atomicAdd(count + (int64_t)leaf[k] * kCountStride, 1);
 		}
 	}
+	int n_over = 0;  // this thread's queries whose bucket was full
 #pragma unroll
 	for (int k = 0; k < kItems; k++) {
 		if (!live[k]) continue;
@@ -114,16 +142,9 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(DeviceModel m, cons
 #pragma unroll
 			for (int d = 0; d < RS; d += 4) st_sector_cg(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
 			}
-		} else {
-			// one atomic per warp on the list counter (a skewed batch sends most of a warp here)
-			const unsigned peers = __activemask();
-			const int leader = __ffs(peers) - 1, lane_id = threadIdx.x & 31;
-			int base = 0;
-			if (lane_id == leader) base = atomicAdd(n_ovf, __popc(peers));
-			base = __shfl_sync(peers, base, leader);
-			ovf[base + __popc(peers & ((1u << lane_id) - 1))] = (int32_t)i;
-		}
+		} else n_over++;
 	}
+	append_overflow<kItems>(n_over, live, slot, cap, i0, ovf, n_ovf);
 }
 
 // The same pass for the COMMON model shape, checked on the host (scatter_fast_ok): every domain width a power of two, a
@@ -198,13 +219,14 @@ __global__ void __launch_bounds__(256) bucket_scatter_fast_kernel(DeviceModel m,
 			const unsigned peers = __match_any_sync(0xffffffffu, key);
 			const int leader = __ffs(peers) - 1;
 			int base = 0;
-			if (live[k] && lane_id == leader) base = atomicAdd(count + leaf[k], __popc(peers));
+			if (live[k] && lane_id == leader) base = atomicAdd(count + (int64_t)leaf[k] * kCountStride, __popc(peers));
 			base = __shfl_sync(0xffffffffu, base, leader);
 			slot[k] = base + __popc(peers & ((1u << lane_id) - 1));
 		} else {
-			if (live[k]) slot[k] = atomicAdd(count + leaf[k], 1);
+			if (live[k]) slot[k] = atomicAdd(count + (int64_t)leaf[k] * kCountStride, 1);
 		}
 	}
+	int n_over = 0;
 #pragma unroll
 	for (int k = 0; k < kItems; k++) {
 		if (!live[k]) continue;
@@ -217,15 +239,9 @@ __global__ void __launch_bounds__(256) bucket_scatter_fast_kernel(DeviceModel m,
 			double *row = rec + ((int64_t)leaf[k] * cap + slot[k]) * RS;
 #pragma unroll
 			for (int d = 0; d < RS; d += 4) st_sector_cg(row + d, v[d], v[d + 1], v[d + 2], v[d + 3]);
-		} else {
-			const unsigned peers = __activemask();
-			const int leader = __ffs(peers) - 1;
-			int base = 0;
-			if (lane_id == leader) base = atomicAdd(n_ovf, __popc(peers));
-			base = __shfl_sync(peers, base, leader);
-			ovf[base + __popc(peers & ((1u << lane_id) - 1))] = (int32_t)i;
-		}
+		} else n_over++;
 	}
+	append_overflow<kItems>(n_over, live, slot, cap, i0, ovf, n_ovf);
 }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 	int32_t leaf = blockIdx.x * 8 + warp, n = 0;
 	int buf = 0;
 	if (leaf < m.L) {
-		n = min(count[leaf], cap);
+		n = min(count[(int64_t)leaf * kCountStride], cap);
 		issue_block(leaf, slot0);
 		load_rec(rec + ((int64_t)leaf * cap + lane) * RS);  // a bucket has >= 32 slots; lanes beyond n read unused memory
 	}
@@ -285,11 +301,11 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 		const int32_t next = leaf + n_warps;
 		const bool more = next < m.L;
 		int32_t n_next = 0;
-		if (more) n_next = count[next];
+		if (more) n_next = count[(int64_t)next * kCountStride];
 		if (DBL && more) { issue_block(next, slot0 + (buf ^ 1) * slot_doubles); cp_async_wait<1>(); }
 		else cp_async_wait<0>();
 		__syncwarp();
-		if (lane == 0 && n > 0) count[leaf] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
+		if (lane == 0 && n > 0) count[(int64_t)leaf * kCountStride] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
 		const double *blk = slot0 + (DBL ? buf : 0) * slot_doubles;
 		const double *bucket = rec + (int64_t)leaf * cap * RS;
 		const double *nbucket = rec + ((int64_t)next * cap + lane) * RS;
@@ -381,13 +397,13 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_bulk_kernel(DeviceModel m,
 	int32_t leaf = blockIdx.x * 8 + warp;
 	Item cur{leaf, 0, 0, 0};
 	if (leaf < m.L) {
-		const int32_t n = min(count[leaf], cap);
-		if (lane == 0 && n > 0) count[leaf] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
+		const int32_t n = min(count[(int64_t)leaf * kCountStride], cap);
+		if (lane == 0 && n > 0) count[(int64_t)leaf * kCountStride] = 0;  // ready for the next chunk (the scatter pass of this chunk has finished)
 		cur = first_item(leaf, n);
 	}
 	// the count of the leaf AFTER the next one is read one item early (its global round trip is hidden as well)
 	int32_t n_ahead = 0, leaf_ahead = leaf + n_warps;
-	if (leaf_ahead < m.L) n_ahead = count[leaf_ahead];
+	if (leaf_ahead < m.L) n_ahead = count[(int64_t)leaf_ahead * kCountStride];
 	uint32_t phase = 0;  // bit b: parity to wait for on bar[warp][b]
 	int b = 0;
 	issue(cur, 0);
@@ -402,11 +418,11 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_bulk_kernel(DeviceModel m,
 			int32_t n = 0;
 			if (nl < m.L) {
 				n = min(n_ahead, cap);
-				if (lane == 0 && n > 0) count[nl] = 0;
+				if (lane == 0 && n > 0) count[(int64_t)nl * kCountStride] = 0;
 			}
 			nxt = first_item(nl, n);
 			leaf_ahead = nl + n_warps;
-			n_ahead = leaf_ahead < m.L ? count[leaf_ahead] : 0;
+			n_ahead = leaf_ahead < m.L ? count[(int64_t)leaf_ahead * kCountStride] : 0;
 		}
 		if (nxt.leaf < m.L) issue(nxt, b ^ 1);
 		// ---- this item, from shared memory
@@ -525,7 +541,7 @@ bool bucket_path_supported(const DeviceModel &m) { return m.D == 1 && m.tensor_F
 
 size_t bucket_work_bytes(const DeviceModel &m, int64_t chunk)
 {
-	const size_t ints = (size_t)m.L + 4 + (size_t)chunk;
+	const size_t ints = (size_t)m.L * kCountStride + 4 + (size_t)chunk;
 	return ((ints * sizeof(int32_t) + 127) & ~(size_t)127) + (size_t)m.L * bucket_capacity(m, chunk) * brec_doubles(m.N) * sizeof(double) + 256;
 }
 BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base)
@@ -536,7 +552,7 @@ BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base)
 	w.bulk = true;
 	w.fast = true;
 	int32_t *p = reinterpret_cast<int32_t *>(base);
-	w.count = p; p += m.L;
+	w.count = p; p += (size_t)m.L * kCountStride;
 	w.n_ovf = p; p += 4;
 	w.ovf = p; p += chunk;
 	const size_t ints = (size_t)(p - reinterpret_cast<int32_t *>(base));
@@ -546,7 +562,7 @@ BucketWork carve_bucket_work(const DeviceModel &m, int64_t chunk, void *base)
 }
 int launch_bucket_reset(const DeviceModel &m, const BucketWork &w, cudaStream_t st)
 {
-	cudaMemsetAsync(w.count, 0, ((size_t)m.L + 4) * sizeof(int32_t), st);
+	cudaMemsetAsync(w.count, 0, ((size_t)m.L * kCountStride + 4) * sizeof(int32_t), st);
 	return 0;
 }
 

@@ -425,7 +425,7 @@ def test_error_check_nan_component_is_sticky():
 
 def test_adaptive_dispatch_between_buckets_and_counting_sort():
     """Automatic path selection for big scalar batches on tensor-product leaves: uniform batches take the single-pass leaf
-    buckets; once the batches seen so far overflow the buckets' capacity (skewed batches) the next calls take the exact
+    buckets; once most of the batches seen so far (> 65 %) overflows the buckets' capacity (lattice sweeps, trajectories) the next calls take the exact
     counting sort, and go back when the batches turn uniform again.  Decided from counters the kernels keep (no
     synchronisation), so a switch takes effect a call later; results are the same on every path."""
     torch = _torch()
@@ -434,7 +434,8 @@ def test_adaptive_dispatch_between_buckets_and_counting_sort():
     gen = torch.Generator("cuda").manual_seed(31)
     uniform = torch.rand((Q, 3), dtype=torch.float64, device="cuda", generator=gen)
     skewed = uniform.clone()
-    skewed[::2] = skewed[::2] * 0.1 + 0.45   # half of the batch in 0.1 % of the domain
+    sel = torch.arange(Q, device="cuda") % 10 != 0
+    skewed[sel] = skewed[sel] * 0.1 + 0.45   # nine tenths of the batch in 0.1 % of the domain (the switch needs > 65 % overflow)
     st = torch.cuda.current_stream().cuda_stream
 
     def run(tq):
