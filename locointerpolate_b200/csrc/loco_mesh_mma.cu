@@ -44,6 +44,12 @@ constexpr int MM_D = 128;     // value components per chunk
 constexpr int MM_K = 16;      // value rows per stage
 constexpr int MM_NS_MULTI = 4; // stages in flight when a chunk needs several stages (2 CTAs of ~100 KB per SM)
 constexpr int MM_NS_ONE = 4;   // ... when all K <= 16 rows fit one stage: the weights are per item, a stage is value rows only
+// !ONE: who applies the stage's high factor to the low-dimension weight products.  true: the (otherwise idle) producers write
+// the stage's 16 x 64 weights w = low * high into a per-stage buffer (16 independent multiplies per lane; 3 stages fit);
+// false: the consumers scale their A fragments (4 stages, but every one of the 4 warps sharing a query block repeats the
+// multiplies: 128 instead of 32 warp-level DMULs per stage on the pipe the DMMAs need -- ncu r02h: 8 x 2.3 % of the samples).
+// Measured equal (c4b 40.7 k vs 40.8 k q/s, c4 91.6 k vs 94.1 k): the consumer-side form with its deeper ring is kept.
+constexpr bool MM_PSCALE = false;
 constexpr bool MM_TMA_STORE = false;  // results through shared memory + TMA bulk stores (measured: no gain over direct 256-bit stores, costs a stage)
 constexpr int MM_STG_LD = 40;  // row stride (doubles) of a warp's 8 x 32 result staging block: conflict-free 128-bit stores, 16-byte aligned rows
 constexpr int MM_CONSUMERS = 8;
@@ -91,14 +97,16 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 	// "high" product is constant over runs of LOWK consecutive rows
 	constexpr int LOWD = NT < (CUBIC ? 2 : 4) ? NT : (CUBIC ? 2 : 4);
 	constexpr int LOWK = 1 << (LOGF * LOWD);
-	constexpr int MM_NS = ONE ? MM_NS_ONE : MM_NS_MULTI;
-	constexpr int MM_NW = 2;  // weight buffers: per item (all rows of a chunk when ONE, the low-dimension products otherwise)
+	constexpr bool PSCALE = MM_PSCALE && !ONE;
+	constexpr int MM_NS = ONE ? MM_NS_ONE : (PSCALE ? 3 : MM_NS_MULTI);
+	constexpr int MM_NW = PSCALE ? MM_NS : 2;  // weight buffers: per stage (PSCALE), else per item (all rows of a chunk when ONE, the low-dimension products otherwise)
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *sV = reinterpret_cast<double *>(smem_raw);             // [MM_NS][MM_K][MM_LDV]
 	double *sW = sV + MM_NS * MM_K * MM_LDV;                       // [MM_NW][MM_K][MM_LDW]
 	double *sF = sW + MM_NW * MM_K * MM_LDW;                       // [NT*F][MM_Q]   producer only
-	double *sH = sF + NT * F * MM_Q;                               // [MM_NS][MM_Q]  the stage's high factor of every query (!ONE)
-	int32_t *sQi = reinterpret_cast<int32_t *>(sH + MM_NS * MM_Q); // [2][MM_Q]      double-buffered per item: read by the consumers' epilogues
+	double *sH = sF + NT * F * MM_Q;                               // [MM_NS][MM_Q]  the stage's high factor of every query (!ONE, !PSCALE)
+	double *sWl = sH + MM_NS * MM_Q;                               // [MM_K][MM_Q]   the item's low-dimension products, producer-private (PSCALE)
+	int32_t *sQi = reinterpret_cast<int32_t *>(sWl + (PSCALE ? MM_K * MM_Q : 0)); // [2][MM_Q]  double-buffered per item: read by the consumers' epilogues
 	double *sStage = reinterpret_cast<double *>(sQi + 2 * MM_Q);   // [MM_CONSUMERS][8][MM_STG_LD]  (ONE only) results on their way to TMA bulk stores
 	__shared__ __align__(8) uint64_t full_bar[MM_NS], empty_bar[MM_NS], item_bar[2];
 	__shared__ ItemGeom s_item[2];  // the producers locate the item's leaf (a binary search over tile offsets); the consumers read it here
@@ -165,7 +173,8 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 #pragma unroll
 			for (int d = 0; d < LOWD; d++) lowK *= nd[d];
 			{
-				double *W_ = sW + (size_t)ib * MM_K * MM_LDW + q;
+				double *W_ = PSCALE ? sWl + q : sW + (size_t)ib * MM_K * MM_LDW + q;
+				constexpr int W_LD = PSCALE ? MM_Q : MM_LDW;
 				int dig[LOWD];
 #pragma unroll
 				for (int d = 0; d < LOWD; d++) dig[d] = 0;
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 							dig[d] = 0;
 						}
 					}
-					W_[kl * MM_LDW] = w;
+					W_[kl * W_LD] = w;
 				}
 			}
 			const int32_t K = ig.K;
@@ -222,11 +231,21 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 #pragma unroll
 					for (int d = LOWD; d < NT; d++) ph *= sF[(d * F + hd[d - LOWD]) * MM_Q + q];
 				}
+				double wreg[PSCALE ? MM_K : 1];
+				if constexpr (PSCALE) {
+#pragma unroll
+					for (int kk = 0; kk < MM_K; kk++) wreg[kk] = sWl[kk * MM_Q + q] * ph;  // rows >= lowK are zero
+				}
 				const int32_t row = my_row;
 				if (pw == 0 && s + 1 < n_steps) my_row = row_of((c + 1 == n_stages) ? 0 : c + 1, lane);  // row index of the NEXT step's copy
 				mbar_wait(&empty_bar[st], ((g / MM_NS) & 1u) ^ 1u);
-				if (!ONE) sH[st * MM_Q + q] = ph;
-				__syncwarp();  // every lane's factor is written before lane 0 arrives on the stage barrier
+				if constexpr (PSCALE) {
+					double *Ws = sW + (size_t)st * MM_K * MM_LDW + q;
+#pragma unroll
+					for (int kk = 0; kk < MM_K; kk++)
+						if (kk < kc4) Ws[kk * MM_LDW] = wreg[kk];
+				} else if (!ONE) sH[st * MM_Q + q] = ph;
+				__syncwarp();  // every lane's weights / factor are written before lane 0 arrives on the stage barrier
 				if (pw == 0) {
 					// ---- the stage's value rows: one TMA bulk copy per row segment
 					const int32_t d0 = (ig.dc0 + dc) * MM_D;
@@ -262,7 +281,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 		const int32_t K = ig.K;
 		const int n_stages = ONE ? 1 : K / ig.lowK;
 		const int n_steps = ig.n_dc * n_stages;
-		const int n_mi = min(4, (ig.nq - wq * 32 + 7) >> 3);  // 8-query blocks beyond the tile's last query hold only padding
+		// the tile's 8-query blocks are dealt alternately to the two warp rows (block b = 2*mi + wq): a partially filled tile
+		// (the last tile of most leaves) keeps BOTH rows busy instead of leaving warps 4-7 idle below 33 queries; blocks beyond
+		// the tile's last query hold only padding and are skipped
+		const int n_mi = max(0, min(4, (((ig.nq + 7) >> 3) - wq + 1) >> 1));
 		for (int s = 0; s < n_steps; s++, g++) {
 			const int dc = s / n_stages, c = s - dc * n_stages;
 			const int st = g % MM_NS;
@@ -274,19 +296,19 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 			}
 			mbar_wait(&full_bar[st], (g / MM_NS) & 1u);
 			const int kc = ((ONE ? min(MM_K, K) : ig.lowK) + 3) & ~3;  // padded to whole MMA k-steps with zero weights
-			const double *w_base = sW + (size_t)ib * MM_K * MM_LDW + wq * 32 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr]
+			const double *w_base = sW + (size_t)(PSCALE ? st : ib) * MM_K * MM_LDW + wq * 8 + fr;  // A[fr][fc] = W[k0 + fc][q0 + fr], q0 = (2*mi + wq) * 8
 			const double *v_base = sV + (size_t)st * MM_K * MM_LDV + wd * 32 + fr;  // B[fc][fr] = V[k0 + fc][d0 + fr]
 			if (n_mi > 0) {
 				double hq[4];  // the stage's high factor of this lane's four fragment rows (queries)
 #pragma unroll
-				for (int mi = 0; mi < 4; mi++) hq[mi] = ONE ? 1.0 : sH[st * MM_Q + wq * 32 + mi * 8 + fr];
+				for (int mi = 0; mi < 4; mi++) hq[mi] = (ONE || PSCALE) ? 1.0 : sH[st * MM_Q + (2 * mi + wq) * 8 + fr];
 #pragma unroll 2
 				for (int k0 = 0; k0 < kc; k0 += 4) {
 					double a[4], bf[4];
 #pragma unroll
 					for (int mi = 0; mi < 4; mi++) {
-						a[mi] = w_base[(k0 + fc) * MM_LDW + mi * 8];
-						if (!ONE) a[mi] *= hq[mi];  // w = low * high: the product the reference's weight is
+						a[mi] = w_base[(k0 + fc) * MM_LDW + mi * 16];
+						if (!ONE && !PSCALE) a[mi] *= hq[mi];  // w = low * high: the product the reference's weight is
 					}
 #pragma unroll
 					for (int ni = 0; ni < 4; ni++) bf[ni] = v_base[(k0 + fc) * MM_LDV + ni * 8];
@@ -318,9 +340,9 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 						fence_async_smem();
 						__syncwarp();
 						if (lane < 8) {
-							const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + lane];
+							const int32_t qi = sQi[ib * MM_Q + (2 * mi + wq) * 8 + lane];
 							if (qi >= 0) {
-								const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + lane - ring_base : (int64_t)qi;
+								const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + (2 * mi + wq) * 8 + lane - ring_base : (int64_t)qi;
 								tma_bulk_s2g(out + orow * out_stride + d0 + wd * 32, stg + lane * MM_STG_LD, 32 * 8);
 							}
 							tma_bulk_commit();
@@ -332,8 +354,8 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 					const bool odd = fc & 1;
 #pragma unroll
 					for (int mi = 0; mi < 4; mi++) {
-						const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
-						const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
+						const int32_t qi = sQi[ib * MM_Q + (2 * mi + wq) * 8 + fr];
+						const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + (2 * mi + wq) * 8 + fr - ring_base : (int64_t)qi;
 						double *o = out + orow * out_stride + d0 + wd * 32;
 #pragma unroll
 						for (int p = 0; p < 2; p++) {
@@ -354,9 +376,9 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 				} else {
 #pragma unroll
 				for (int mi = 0; mi < 4; mi++) {
-					const int32_t qi = sQi[ib * MM_Q + wq * 32 + mi * 8 + fr];
+					const int32_t qi = sQi[ib * MM_Q + (2 * mi + wq) * 8 + fr];
 					if (qi < 0) continue;
-					const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + wq * 32 + mi * 8 + fr - ring_base : (int64_t)qi;
+					const int64_t orow = ring_base >= 0 ? (int64_t)ig.qbeg + (2 * mi + wq) * 8 + fr - ring_base : (int64_t)qi;
 					double *o = out + orow * out_stride + d0;
 #pragma unroll
 					for (int ni = 0; ni < 4; ni++) {
@@ -380,9 +402,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mesh_tensor_mma_kernel(DeviceMo
 namespace {
 size_t mma_smem_bytes(int N, int F, int lowk, bool one)
 {
-	const int ns = one ? MM_NS_ONE : MM_NS_MULTI, nw = 2;
+	const bool pscale = MM_PSCALE && !one;
+	const int ns = one ? MM_NS_ONE : (pscale ? 3 : MM_NS_MULTI), nw = pscale ? ns : 2;
 	(void)lowk;
-	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + ns * MM_Q) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64 +
+	return (size_t)(ns * MM_K * MM_LDV + nw * MM_K * MM_LDW + N * F * MM_Q + ns * MM_Q + (pscale ? MM_K * MM_Q : 0)) * sizeof(double) + 2 * MM_Q * sizeof(int32_t) + 64 +
 	       ((one && MM_TMA_STORE) ? (size_t)MM_CONSUMERS * 8 * MM_STG_LD * sizeof(double) : 0);
 }
 template <int NT, bool CUBIC, bool EXACT, bool ONE>

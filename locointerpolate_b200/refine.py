@@ -55,15 +55,28 @@ def select_splits(model: Model, threshold: float, max_level: int, literal_cyclic
 
 
 def adaptive_sample_passes(get_model: Callable[[], Model], surgery: Callable[[int, int], None], threshold: float, max_level: int,
-                           max_passes: int = 256, literal_cyclic: bool = False) -> List[dict]:
+                           max_passes: int = 256, literal_cyclic: bool = False, get_graph: Callable[[], object] = None,
+                           device: int = 0) -> List[dict]:
     """Level-synchronous adaptiveSample: repeat {flatten -> batched error check on the device -> host surgery on the
     flagged leaves of the largest size class} until no leaf is flagged.  `get_model()` returns the model of the grid's
-    current state (from_graph of whatever the host's grid serialises to); `surgery(leaf, direction)` is refineCell."""
+    current state (from_graph of whatever the host's grid serialises to); `surgery(leaf, direction)` is refineCell.
+
+    Incremental form: pass `get_graph()` (-> capi.GraphArrays of the grid's current state) instead of `get_model`
+    (get_model=None).  The first pass creates the handle; later passes call Model.update_from_graph on it
+    (loco_model_update_from_graph): leaves outside the split cells' doubly-adjacent sets keep their evaluation cells."""
     log = []
+    model = None
     for _ in range(max_passes):
-        model = get_model()
+        if get_graph is not None:
+            if model is None:
+                model = Model.from_graph(get_graph(), device=device)
+            else:
+                model.update_from_graph(get_graph())
+        else:
+            model = get_model()
         leaves, dirs, err = select_splits(model, threshold, max_level, literal_cyclic)
-        log.append({"leaves": model.L, "flagged": len(leaves), "max_center_error": float(np.nanmax(err)) if len(err) else 0.0})
+        log.append({"leaves": model.L, "flagged": len(leaves), "max_center_error": float(np.nanmax(err)) if len(err) else 0.0,
+                    "reused_leaves": int(model.info.get("n_reused_leaves", 0))})
         if not leaves:
             return log
         for leaf, direction in zip(leaves, dirs):

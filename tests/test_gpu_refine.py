@@ -50,3 +50,36 @@ def test_level_synchronous_refinement_with_reference_surgery(basis, max_level, t
     s_out, _, s_status = seq.sampled_function().eval(q)
     e_pass, e_seq = np.abs(out[ok] - truth[ok]).max(), np.abs(s_out[s_status == 0] - truth[s_status == 0]).max()
     assert e_pass <= 2.0 * max(e_seq, threshold), (e_pass, e_seq, log[-1]["leaves"], seq.num_leaves())
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref (the compiled reference) is not built")
+def test_refinement_loop_on_one_handle_updated_incrementally():
+    """The same loop with ONE device handle that is updated in place after every pass (loco_model_update_from_graph): the
+    pass decisions and the final evaluation must equal those of the loop that builds a fresh handle per pass."""
+    threshold, max_level = 0.1, 7
+
+    def run(incremental):
+        grid = refapi.RefGrid(2, capi.CUBIC, False, 0, threshold, 2)
+        graph = lambda: oracleapi.graph_from_ref(grid.sampled_function().graph())
+        if incremental:
+            log = refine.adaptive_sample_passes(None, grid.refine, threshold, max_level, get_graph=graph, device=0)
+        else:
+            log = refine.adaptive_sample_passes(lambda: capi.Model.from_graph(graph(), device=0), grid.refine, threshold, max_level)
+        return grid, log
+    g_inc, log_inc = run(True)
+    g_new, log_new = run(False)
+    assert [(p["leaves"], p["flagged"]) for p in log_inc] == [(p["leaves"], p["flagged"]) for p in log_new]
+    assert np.allclose([p["max_center_error"] for p in log_inc], [p["max_center_error"] for p in log_new], rtol=0, atol=1e-13)
+    assert max(p["reused_leaves"] for p in log_inc) > 0 and all(p["reused_leaves"] == 0 for p in log_new)
+    # one more update of a handle, then evaluation against a fresh handle of the same state: identical
+    ga = oracleapi.graph_from_ref(g_inc.sampled_function().graph())
+    m = capi.Model.from_graph(oracleapi.graph_from_ref(refapi.RefGrid(2, capi.CUBIC, False, 0, threshold, 2).sampled_function().graph()), device=0)
+    m.update_from_graph(ga)
+    fresh = capi.Model.from_graph(ga, device=0)
+    q = np.random.default_rng(5).random((300_000, 2))
+    for path in (0, 1, 4):
+        m.set_option("path", path)
+        fresh.set_option("path", path)
+        a, la, sa = m.eval(q)
+        b, lb, sb = fresh.eval(q)
+        assert np.array_equal(la, lb) and np.array_equal(sa, sb) and np.array_equal(a, b, equal_nan=True), path
