@@ -453,6 +453,10 @@ def measure(name, w, args, rank, world, local, config, full, secondary=False):
         if flush is not None:
             flush.zero_()
         step(i)
+        if w.get("dist"):
+            # skewed batches: the library picks its sort path from the counters of the batches it has FINISHED (no synchronisation
+            # inside the call); a real stream of batches has that history, a back-to-back enqueue of the warm-up would not
+            torch.cuda.synchronize()
     if ex is not None:
         ex.drain()
     torch.cuda.synchronize()
