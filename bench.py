@@ -629,7 +629,8 @@ def traffic_for(name, kernel, q_per_launch):
     try:
         from locointerpolate_b200 import build as product_build
         tj = json.load(open(tpath))
-        ent = tj.get(name, {})
+        # entries are keyed "<workload>" or "<workload>_<anything>" (one per captured kernel of that workload)
+        ent = next((v for k, v in tj.items() if (k == name or k.startswith(name + "_")) and v.get("kernel") == kernel), {})
         if ent.get("kernel") != kernel:
             return None, f"no ncu capture of {kernel} for workload {name}"
         digest = product_build.source_digest()[:16]
