@@ -301,6 +301,19 @@ public:
 		return LCError();
 	}
 
+	// The same object after the host refined its grid (LCAdaptiveGrid::refineCell, LCAdaptiveGrid.cpp:629-914): re-flatten
+	// from the grid's new state, described as plain arrays (INTEGRATION.md section B shows how a reference-side binding
+	// fills loco_graph_t).  Incremental: leaves outside the split cells' doubly-adjacent sets keep their evaluation cells
+	// (loco_model_update_from_graph); getNReusedLeaves() tells how many.
+	LCError updateFromGraph(const loco_graph_t &graph)
+	{
+		if (!ok()) return LCError("no model attached");
+		if (loco_model_update_from_graph(model_->m, &graph)) return loco_detail::last_error(model_->m);
+		if (loco_model_info(model_->m, &info_)) return loco_detail::last_error(model_->m);
+		return LCError();
+	}
+	int64_t getNReusedLeaves() const { return info_.n_reused_leaves; }
+
 	LCAdaptiveGridCell *getRoot() { return &root_; }
 	std::vector<LCSample *> getSamples() { return std::vector<LCSample *>(); }
 	std::vector<LCAdaptiveGridCell *> getBorderCells() { return std::vector<LCAdaptiveGridCell *>(); }

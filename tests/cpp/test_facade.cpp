@@ -263,11 +263,106 @@ static void vectorValuedTest()
 	CHECK(ok && worst < 1e-13, "components 0 and 1 equal the scalar interpolant of f and 2f (linearity of the weighted sum)");
 }
 
+// The host that owns the grid refines it and hands the new state over as plain arrays (loco_graph_t); the function object
+// stays the same.  A 1-D linear grid is small enough to write down by hand: n = 2^level cells over [-1,1], samples on the
+// n+1 lattice points with one unit-weight hat each of support 2/n (LCAdaptiveGrid.cpp:268-296), cells in pre-order with
+// midpoint splits (:234-249), each leaf listing its two corner samples (:212-231).
+struct Grid1D {
+	std::vector<double> domain, centers, values, support, weight, ranges, splitVal;
+	std::vector<int64_t> bfOff, cellOff;
+	std::vector<int32_t> splitDir, child2, cellSample;
+	loco_graph_t desc;
+
+	void cell(double lo, double hi, int j0, int nj, const std::vector<int> &leafSample)
+	{
+		const size_t me = splitDir.size();
+		ranges.push_back(lo); ranges.push_back(hi);
+		splitDir.push_back(-1); splitVal.push_back(0.0); child2.push_back(-1);
+		if (nj == 1) {
+			cellSample.push_back(leafSample[j0]); cellSample.push_back(leafSample[j0 + 1]);
+			cellOff.push_back((int64_t)cellSample.size());
+			return;
+		}
+		cellOff.push_back((int64_t)cellSample.size());
+		const double mid = 0.5 * (lo + hi);
+		splitDir[me] = 0; splitVal[me] = mid;
+		cell(lo, mid, j0, nj / 2, leafSample);
+		child2[me] = (int32_t)splitDir.size();
+		cell(mid, hi, j0 + nj / 2, nj / 2, leafSample);
+	}
+
+	Grid1D(int level, int basisType, double lo, double hi, double (*f)(double))
+	{
+		const int n = 1 << level;
+		domain = {lo, hi};
+		std::vector<int> ids;
+		bfOff.push_back(0);
+		for (int j = 0; j <= n; j++) {
+			const double alpha = (double)j / n, c = -(1.0 - alpha) + alpha;
+			centers.push_back(c);
+			values.push_back(f(lo * (1 - (c + 1) / 2) + hi * ((c + 1) / 2)));
+			support.push_back(2.0 / n); weight.push_back(1.0);
+			bfOff.push_back(j + 1);
+			ids.push_back(j);
+		}
+		cellOff.push_back(0);
+		cell(-1.0, 1.0, 0, n, ids);
+		std::memset(&desc, 0, sizeof desc);
+		desc.n_params = 1; desc.value_dim = 1; desc.basis_type = basisType; desc.domain = domain.data();
+		desc.n_samples = n + 1; desc.sample_center = centers.data(); desc.sample_value = values.data();
+		desc.bf_offset = bfOff.data(); desc.bf_center = centers.data(); desc.bf_support = support.data(); desc.bf_weight = weight.data();
+		desc.n_cells = (int64_t)splitDir.size(); desc.cell_ranges = ranges.data(); desc.cell_split_dir = splitDir.data();
+		desc.cell_split_val = splitVal.data(); desc.cell_child2 = child2.data();
+		desc.cell_sample_offset = cellOff.data(); desc.cell_sample = cellSample.data();
+	}
+};
+
+static double bumpy(double x) { return std::sin(2.5 * x) + 0.3 * x * x; }
+
+static void updateFromGraphTest(bool hostOnly)
+{
+	std::printf("updateFromGraph (1-D linear grid, 2 -> 8 cells)\n");
+	const double lo = 0.5, hi = 2.5;
+	Grid1D coarse(1, LOCO_LINEAR_BSPLINE, lo, hi, bumpy), fine(3, LOCO_LINEAR_BSPLINE, lo, hi, bumpy), other(3, LOCO_CUBIC_BSPLINE, lo, hi, bumpy);
+	loco_model_t *h = nullptr;
+	CHECK(loco_model_from_graph(&coarse.desc, hostOnly ? LOCO_HOST_ONLY : 0, &h) == LOCO_OK && h, "model from the coarse grid");
+	if (!h) return;
+	LCSampledFunction f(h);
+	CHECK(f.getNLeaves() == 2 && f.getNSamples() == 3, "2 leaves, 3 samples");
+	LCError bad = f.updateFromGraph(other.desc);
+	CHECK(!bad.isOK() && bad.internalDescription().find("same function") != std::string::npos, "a state with another basis type is refused");
+	CHECK(f.getNLeaves() == 2, "and the refused update left the object as it was");
+	CHECK(f.updateFromGraph(fine.desc).isOK(), "updateFromGraph to the refined state");
+	CHECK(f.getNLeaves() == 8 && f.getNSamples() == 9, "8 leaves, 9 samples after the update");
+	CHECK(f.getMinRange(0) == lo && f.getMaxRange(0) == hi, "the domain is kept");
+	if (hostOnly) return;
+	// the interpolant of the refined state: piecewise linear through f at the 9 lattice points
+	const int nq = 97;
+	std::vector<double> q(nq), out(nq);
+	std::vector<int32_t> leaf(nq);
+	std::vector<uint8_t> st(nq);
+	for (int i = 0; i < nq; i++) q[i] = lo + (hi - lo) * (i + 0.37) / nq;
+	CHECK(f.evalShapeInfoBatch(q.data(), nq, out.data(), leaf.data(), st.data()).isOK(), "evalShapeInfoBatch on the updated object");
+	double worst = 0;
+	bool okAll = true, leavesOk = true;
+	for (int i = 0; i < nq; i++) {
+		const double u = (q[i] - lo) / (hi - lo) * 8;
+		const int c = (int)u;
+		const double a = u - c, x0 = lo + (hi - lo) * c / 8, x1 = lo + (hi - lo) * (c + 1) / 8;
+		worst = std::fmax(worst, std::fabs(out[i] - ((1 - a) * bumpy(x0) + a * bumpy(x1))));
+		okAll = okAll && st[i] == LOCO_ST_OK;
+		leavesOk = leavesOk && leaf[i] == c;  // leaves are numbered in pre-order = left to right in one dimension
+	}
+	CHECK(okAll && leavesOk, "every query is located in its cell of the refined grid");
+	CHECK(worst <= 1e-12, "values equal the piecewise-linear interpolant of the refined state within 1e-12");
+}
+
 int main(int argc, char **argv)
 {
 	if (argc < 3) { std::printf("usage: %s <golden .pb> <dump file> [--host-only]\n", argv[0]); return 2; }
 	const bool hostOnly = argc > 3 && !std::strcmp(argv[3], "--host-only");
 	protoTest(argv[1], argv[2], hostOnly);
+	updateFromGraphTest(hostOnly);
 	if (!hostOnly) {
 		linearPrecisionTest(1, LCBasisFunction::CUBIC_BSPLINE, 2);
 		linearPrecisionTest(3, LCBasisFunction::CUBIC_BSPLINE, 1);
