@@ -448,26 +448,29 @@ __device__ __forceinline__ double term_deriv(const double *__restrict__ cs, doub
 	return value * weight;
 }
 
-// LCSampledFunction::evalDeriv on a cubic tensor-product leaf: the leaf's terms are the F^N products of one-dimensional
+// LCSampledFunction::evalDeriv on a tensor-product leaf: the leaf's terms are the F^N products of one-dimensional
 // factors, so the derivative along `dir` is the same contraction with the factors of that dimension replaced by
-// LCCubicBSpline::evalDeriv's one-dimensional derivative (cubic_1d_deriv).  `blk` may be in shared or global memory.
-template <int NT, bool EXACT>
+// LC{Cubic,Linear}BSpline::evalDeriv's one-dimensional derivative (cubic_1d_deriv / the literal linear_1d_ref_deriv, whose
+// signed comparison also changes the factors of the OTHER dimensions).  `blk` may be in shared or global memory.
+template <int NT, bool CUBIC, bool EXACT>
 __device__ __forceinline__ double tensor_eval_scalar_deriv(const DeviceModel &m, const double *blk, const Coord<NT> &x, int dir)
 {
-	double f[NT][4];
+	constexpr int F = CUBIC ? 4 : 2;
+	double f[NT][F];
 #pragma unroll
 	for (int d = 0; d < NT; d++) {
-		const double r = blk[NT * 4 + d];
+		const double r = blk[NT * F + d];
 		const double rs = EXACT ? r : 1.0 / r;
 		const double xv = x.get(d);
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const double diff = xv - blk[d * 4 + j];
+		for (int j = 0; j < F; j++) {
+			const double diff = xv - blk[d * F + j];
 			const double u = EXACT ? diff * r : diff / r;
-			f[d][j] = (d == dir) ? cubic_1d_deriv(u, rs) : cubic_1d(u);
+			if constexpr (CUBIC) f[d][j] = (d == dir) ? cubic_1d_deriv(u, rs) : cubic_1d(u);
+			else f[d][j] = linear_1d_ref_deriv(u, rs, d == dir);
 		}
 	}
-	return TensorContract<NT, 4, NT - 1>::run(blk + m.tl_voff, f, m.tensor_K / 4);
+	return TensorContract<NT, F, NT - 1>::run(blk + m.tl_voff, f, m.tensor_K / F);
 }
 
 // same as term_value with the term's (c, s) pairs in SHARED memory (broadcast reads) and the weight

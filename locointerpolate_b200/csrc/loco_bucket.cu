@@ -256,7 +256,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // The three dependent round trips of a leaf (counter -> block + first records -> arithmetic) are software-pipelined ACROSS
 // leaves: while leaf l is evaluated, the counter of leaf l' = l + #warps has been read, its block is on its way into the
 // other shared-memory slot (cp.async) and its first 32 records are loaded during the last record group of l.
-// DERIV (cubic, fp64): the derivative along cube direction `dir` instead of the value (LCSampledFunction::evalDeriv).
+// DERIV (fp64): the derivative along cube direction `dir` instead of the value (LCSampledFunction::evalDeriv).
 template <int NT, bool CUBIC, bool EXACT, bool FP32, bool DBL, bool DERIV>
 __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, const double *__restrict__ rec, int32_t *count, int32_t cap, double *__restrict__ out,
                                                               const double *__restrict__ q, const int32_t *__restrict__ leaf_in, const int32_t *__restrict__ ovf,
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 			else if (more) load_rec(nbucket);
 			if (s < n) {
 				double r;
-				if constexpr (DERIV) r = tensor_eval_scalar_deriv<NT, EXACT>(m, blk, x, dir);
+				if constexpr (DERIV) r = tensor_eval_scalar_deriv<NT, CUBIC, EXACT>(m, blk, x, dir);
 				else if constexpr (FP32) r = tensor_eval_scalar_f32<NT, CUBIC, EXACT>(m, blk, reinterpret_cast<const float *>(blk + m.tl_voff), x);
 				else if (dbg & 2) r = x.get(0);  // EXPERIMENT: no arithmetic
 				else r = poly ? tensor_leaf_value<NT, CUBIC, EXACT>(m, nullptr, blk, leaf, x) : tensor_eval_scalar<NT, CUBIC, EXACT>(m, blk, x);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256, 3) bucket_eval_kernel(DeviceModel m, cons
 		for (int d = 0; d < NT; d++) p[d] = q[(int64_t)i * NT + d];
 		map_to_cube<NT>(m, p, x);
 		const double *gblk = m.tl_block + (int64_t)leaf_in[i] * m.tl_stride;
-		if constexpr (DERIV) out[i] = tensor_eval_scalar_deriv<NT, EXACT>(m, gblk, x, dir);
+		if constexpr (DERIV) out[i] = tensor_eval_scalar_deriv<NT, CUBIC, EXACT>(m, gblk, x, dir);
 		else out[i] = tensor_leaf_value<NT, CUBIC, EXACT>(m, gblk, poly ? m.tl_poly + (int64_t)leaf_in[i] * m.tp_stride : nullptr, leaf_in[i], x);
 	}
 }
@@ -517,11 +517,9 @@ void run_chunk(const DeviceModel &m, const double *q, int64_t Q, double *out, in
 			static const int edbg = getenv("LOCO_EVAL_DBG") ? atoi(getenv("LOCO_EVAL_DBG")) : 0;  // measurement experiments only
 			kern<<<grid, 256, smem, st>>>(m, w.rec, w.count, w.cap, out, q, leaf, w.ovf, n_ovf, n_ovf_next, deriv_dir, w.stats, Q, edbg);
 		};
-		if constexpr (CUBIC) {
-			if (deriv_dir >= 0) {
-				if (dbl) launch(bucket_eval_kernel<NT, true, EXACT, false, true, true>); else launch(bucket_eval_kernel<NT, true, EXACT, false, false, true>);
-				return;
-			}
+		if (deriv_dir >= 0) {
+			if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, true, true>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, false, true>);
+			return;
 		}
 		if (f32) { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, true, false>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, true, false, false>); }
 		else { if (dbl) launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, true, false>); else launch(bucket_eval_kernel<NT, CUBIC, EXACT, false, false, false>); }
@@ -570,7 +568,6 @@ int launch_eval_scalar_bucket_chunk(const DeviceModel &m, const double *q, int64
                                     int sm_count, bool fp32, int parity, cudaStream_t st, int deriv_dir)
 {
 	if (Q <= 0) return 0;
-	if (deriv_dir >= 0 && m.basis != CUBIC_BSPLINE) return 0;  // the derivative variant exists for the cubic basis only (callers check)
 	const bool cubic = m.basis == CUBIC_BSPLINE, exact = m.exact_rcp != 0;
 #define LOCO_BCASE(NT)                                                                                                                   \
 	case NT:                                                                                                                             \

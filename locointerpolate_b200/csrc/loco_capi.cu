@@ -60,6 +60,7 @@ struct Workspace {
 
 struct loco_model {
 	int device = 0;
+	int64_t n_dterms = 0;    // derivative-only terms of the linear basis over all leaves (Flat::dterm_*)
 	bool host_only = false;  // device == LOCO_HOST_ONLY: introspection only, every evaluation call fails
 	bool initial_upload = false;
 	Graph graph;
@@ -291,6 +292,7 @@ int build_device_model(loco_model *m)
 		}
 	}
 	std::vector<int32_t> dterm_off = narrow(m, f.dterm_off, &ok);
+	m->n_dterms = (int64_t)f.dterm_w.size();
 	if (!ok) return fail(m, LOCO_ERR_INVALID, "support / term lists exceed 2^31 entries");
 	if ((rc = upload(m, dterm_off, &dm.dterm_off))) return rc;
 	if ((rc = upload(m, f.dterm_cs, &dm.dterm_cs, 2))) return rc;
@@ -456,8 +458,10 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		const bool big = Q >= (int64_t)dm.L * 24 && Q >= (1 << 16) && leaf_bytes > 96 * 1024;
 		const bool sorted = !in_cube && (m->opt_path == 4 || (m->opt_path == 0 && big));
 		const bool tiles = !in_cube && m->opt_path == 2;
+		// (derivatives with the linear basis: only while no leaf has derivative-only terms -- Flat::dterm_*, hats that lie right of
+		//  a leaf and still count in the reference's signed comparison; the leaf blocks do not hold them)
 		bool bucket = !in_cube && bucket_path_supported(dm) && (m->opt_path == 5 || (m->opt_path == 0 && big && dm.L >= 256)) &&
-		              (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE);
+		              (deriv_dir < 0 || dm.basis == CUBIC_BSPLINE || m->n_dterms == 0);
 		if (bucket && m->opt_path == 0 && m->opt_adaptive && m->h_stats) {
 			// Automatic dispatch between the single-pass leaf buckets (capacity sized for a uniform batch) and the exact counting
 			// sort: the kernels of both paths add {queries beyond a bucket's capacity, queries seen} to host-mapped counters, and
@@ -480,7 +484,7 @@ int eval_device(loco_model *m, Workspace &w, cudaStream_t st, bool in_cube, cons
 		// derivatives on generic leaves with the cubic basis: the sorted path with the derivative factor in its term lists
 		const bool sorted_deriv = deriv_dir >= 0 && !bucket && sorted && dm.basis == CUBIC_BSPLINE && dm.tensor_F == 0;
 		if (deriv_dir >= 0 && !bucket && !sorted_deriv) {
-			// derivatives outside the bucket path (linear basis, generic leaves, small batches): one thread per query
+			// derivatives outside the bucket path (generic leaves with the linear basis, small batches): one thread per query
 			m->launches += launch_eval_deriv_direct(dm, q, Q, deriv_dir, out, leaf, status, st);
 			CUDA_OK(m, cudaGetLastError());
 			return LOCO_OK;

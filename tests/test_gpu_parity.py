@@ -245,16 +245,17 @@ def test_locate_grid_equals_descent_bootstrap(N, basis, level):
     assert leaf1.max() == m.L - 1
 
 
-@pytest.mark.parametrize("N,level,corners", [(3, 4, True), (2, 6, False), (4, 2, True)])
-def test_derivative_throughput_path_equals_direct(N, level, corners):
-    """evalDeriv on cubic tensor-product leaves through the leaf-bucket path (one derivative factor in the contraction)
-    against the thread-per-query term-list kernel, at a batch size where the automatic dispatch picks the buckets; a
-    skewed part of the batch overflows its buckets."""
+@pytest.mark.parametrize("basis,N,level,corners", [(capi.CUBIC, 3, 4, True), (capi.CUBIC, 2, 6, False), (capi.CUBIC, 4, 2, True),
+                                                   (capi.LINEAR, 3, 4, True), (capi.LINEAR, 2, 6, True), (capi.LINEAR, 5, 2, True)])
+def test_derivative_throughput_path_equals_direct(basis, N, level, corners):
+    """evalDeriv on tensor-product leaves through the leaf-bucket path (one derivative factor in the contraction; the linear
+    basis with the reference's signed comparison, LCBasisFunction.cpp:295-332) against the thread-per-query term-list
+    kernel, at a batch size where the automatic dispatch picks the buckets; a skewed part of the batch overflows its buckets."""
     torch = _torch()
 
     def f(p):
         return 1 + np.sin(3 * p + np.arange(len(p))).sum()
-    m = capi.Model.bootstrap(N, capi.CUBIC, level, 1, corners, fn=f, device=0)
+    m = capi.Model.bootstrap(N, basis, level, 1, corners, fn=f, device=0)
     Q = 600_000
     tq = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(17)) * 1.000002 - 0.000001
     tq[:100_000] = tq[:100_000] * 0.05 + 0.3  # concentrated in a few leaves

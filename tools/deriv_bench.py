@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--level", type=int, default=5)
     ap.add_argument("--adaptive", action="store_true", help="the TestDebug adaptive tree instead of the c2 bootstrap grid")
+    ap.add_argument("--linear", action="store_true", help="linear basis on the same bootstrap grid (the reference's signed-distance formula)")
     args = ap.parse_args()
     import torch
     from locointerpolate_b200 import capi
@@ -36,7 +37,7 @@ def main():
         m = capi.Model.from_proto(t.name, device=0)
         os.unlink(t.name)
     else:
-        m = capi.Model.bootstrap(N, capi.CUBIC, args.level, 1, True, fn=f, device=0)
+        m = capi.Model.bootstrap(N, capi.LINEAR if args.linear else capi.CUBIC, args.level, 1, True, fn=f, device=0)
     q = torch.rand((Q, N), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
     out = torch.empty(Q, dtype=torch.float64, device="cuda")
     leaf = torch.empty(Q, dtype=torch.int32, device="cuda")
@@ -61,7 +62,7 @@ def main():
         else:
             res[name]["max_abs_diff_vs_direct"] = float((out - ref).abs().max())
             res[name]["max_abs_value"] = float(ref.abs().max())
-    print(json.dumps({"model": {"leaves": m.L, "N": N}, "queries": Q, "derivative": res}))
+    print(json.dumps({"model": {"leaves": m.L, "N": N, "basis": "linear" if args.linear else "cubic"}, "queries": Q, "derivative": res}))
 
 
 if __name__ == "__main__":
