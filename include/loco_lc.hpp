@@ -10,7 +10,9 @@
 //   LCFunction             (LCFunction/LCFunction.h:20-49)           abstract f: ranges, hypercube maps, evalShapeInfo
 //   LCBasisFunction        (LCAdaptiveSampling/LCBasisFunction.h:19) the type enum only (evaluation lives in the kernels)
 //   LCAdaptiveSamplingParams (LCAdaptiveSamplingParams.h:8-39)       same fields and constructor
-//   LCAdaptiveGrid         (LCAdaptiveGrid.h:18-75)                  bootstrap construction + the decideSplit error check, batched
+//   LCAdaptiveGrid         (LCAdaptiveGrid.h:18-75)                  bootstrap construction, the decideSplit error check batched, and
+//                                                                    adaptiveSample as level-synchronous passes (error check on the GPU,
+//                                                                    refineCell's surgery on the host: loco_grid.hpp)
 //   LCSampledFunction      (LCSampledFunction.h:11-36)               evalShapeInfo (batch of one) + evalShapeInfoBatch
 //   PrecomputedParametricShapeConverter (LCProtoConverter.h:11-21)   loadFromProto / outputToProto
 //
@@ -36,6 +38,7 @@
 #include <vector>
 
 #include "loco_b200.h"
+#include "loco_grid.hpp"
 
 #ifdef LOCO_LC_NAMESPACE
 namespace LOCO_LC_NAMESPACE {
@@ -378,14 +381,17 @@ public:
 };
 
 // ---- LCAdaptiveGrid -----------------------------------------------------------------------------------------
-// The bootstrap phase of the reference's builder (LCAdaptiveGrid.cpp:16-39 -> bootstrapSample :256-456) and the
-// data-parallel part of its refinement loop: decideSplit's error check (:578-626), evaluated for ALL leaves in
-// one batch on the GPU.  The topology surgery of refineCell (:629-914) is not part of this build.
+// The bootstrap phase of the reference's builder (LCAdaptiveGrid.cpp:16-39 -> bootstrapSample :256-456) and its refinement
+// loop (adaptiveSample :481-545) in level-synchronous form: decideSplit's error check (:578-626) for ALL
+// leaves in one batch on the GPU, then refineCell (:629-914; host surgery, loco_grid.hpp) for the flagged leaves of the
+// largest size class, then an incremental re-flatten (loco_model_update_from_graph).  Unlike the reference's constructor,
+// which refines straight away, the constructor here stops after the bootstrap phase (so that the error check of that state
+// can be inspected); call adaptiveSample() to run the loop.
 class LCAdaptiveGrid {
 public:
 	LCAdaptiveGrid(LCFunction *parametricShape, LCBasisFunction::LCBasisFunctionType basisType, LCAdaptiveSamplingParams *params,
 	               bool evalCorners = false, int device = 0)
-	    : params_(params), parametricShape_(parametricShape), basisType_(basisType)
+	    : params_(params), parametricShape_(parametricShape), basisType_(basisType), evalCorners_(evalCorners)
 	{
 		err_ = build(evalCorners, device);
 		if (!err_.isOK()) std::cout << "error in precomputation: " << err_.internalDescription() << std::endl;  // as LCAdaptiveGrid.cpp:28-38
@@ -409,6 +415,14 @@ public:
 	// getJitterPoint's recipe (rand() as float, :564-575), evaluates the true function on the host (it is the
 	// caller's CAD code) and the interpolant on the GPU.
 	LCError decideSplitBatch(std::vector<uint8_t> *split, std::vector<double> *errMax)
+	{
+		LCErrorReturn(errorCheckBatch(split, errMax));
+		const int bootLevel = fn_->getNParams() * params_->bootstrapGridSize_;
+		if (!grid_ && !(bootLevel < params_->maxTreeDepth_)) split->assign(split->size(), 0);  // doSplit = level < maxLevel_ (:584); after adaptiveSample levels differ per leaf
+		return LCError();
+	}
+	// the error part of decideSplit alone: split[l] = !(max(err - threshold) <= 0), without the level limit
+	LCError errorCheckBatch(std::vector<uint8_t> *split, std::vector<double> *errMax)
 	{
 		if (!fn_) return err_;
 		const int64_t L = fn_->getNLeaves();
@@ -441,8 +455,6 @@ public:
 			}
 			if (loco_error_check(m, q.data(), truth.data(), L * P, params_->threshold_, errMax->data(), split->data(), nullptr)) return loco_detail::last_error(m);
 		}
-		const int bootLevel = fn_->getNParams() * params_->bootstrapGridSize_;
-		if (!(bootLevel < params_->maxTreeDepth_)) split->assign((size_t)L, 0);  // doSplit = level < maxLevel_ (:584)
 		return LCError();
 	}
 
@@ -458,13 +470,25 @@ public:
 	{
 		requests->clear();
 		if (!fn || !fn->handle()) return LCError("no model attached");
+		const int64_t L = fn->getNLeaves();
+		std::vector<double> err((size_t)L);
+		std::vector<uint8_t> split((size_t)L);
+		if (loco_center_error(fn->handle(), threshold, err.data(), split.data())) return loco_detail::last_error(fn->handle());
+		LCErrorReturn(selectFromFlags(fn, split, maxLevel, requests));
+		if (errMax) *errMax = std::move(err);
+		return LCError();
+	}
+	// the selection alone, from the flags of any error check (CENTER_BASED or RANDOM_SAMPLES)
+	static LCError selectFromFlags(LCSampledFunction *fn, const std::vector<uint8_t> &split, int maxLevel, std::vector<SplitRequest> *requests)
+	{
+		requests->clear();
+		if (!fn || !fn->handle()) return LCError("no model attached");
 		loco_model_t *m = fn->handle();
 		const int64_t L = fn->getNLeaves();
 		const int N = fn->getNParams();
-		std::vector<double> err((size_t)L), volume((size_t)L), box((size_t)2 * N);
-		std::vector<uint8_t> split((size_t)L);
+		if ((int64_t)split.size() != L) return LCError("one flag per leaf expected");
+		std::vector<double> volume((size_t)L), box((size_t)2 * N);
 		std::vector<int> level((size_t)L), dir((size_t)L);
-		if (loco_center_error(m, threshold, err.data(), split.data())) return loco_detail::last_error(m);
 		double top = 0;
 		for (int64_t l = 0; l < L; l++) {
 			if (loco_leaf_box(m, (int32_t)l, box.data())) return loco_detail::last_error(m);
@@ -482,9 +506,61 @@ public:
 		for (int64_t l = L - 1; l >= 0; l--)
 			if (split[(size_t)l] && level[(size_t)l] < maxLevel && volume[(size_t)l] >= top * (1 - 1e-12))
 				requests->push_back(SplitRequest{(int32_t)l, dir[(size_t)l]});
-		if (errMax) *errMax = std::move(err);
 		return LCError();
 	}
+
+	// LCAdaptiveGrid::adaptiveSample (LCAdaptiveGrid.cpp:481-545) as level-synchronous passes: {error check of ALL leaves on the
+	// GPU (errorCheckBatch: CENTER_BASED or RANDOM_SAMPLES) -> the flagged leaves of the largest size class below
+	// maxTreeDepth_ (what the reference's size-ordered queue pops next) -> refineCell for each of them on the host grid
+	// (loco_grid::Grid, the reference's surgery) -> incremental re-flatten of the model} until no leaf is flagged.
+	// Split direction: ERROR_BASED = getOptimalSplitDirection (LCAdaptiveGridCell.cpp:977-1041) on the host grid's corner
+	// values; CYCLIC = the first dimension of largest extent (decideSplitDirection :553 generalised to N parameters).
+	// The host grid is created on the first call by repeating the bootstrap phase (f is evaluated at the lattice again).
+	LCError adaptiveSample(int *nPasses = nullptr, int64_t *nSplits = nullptr, int maxPasses = 256)
+	{
+		if (nPasses) *nPasses = 0;
+		if (nSplits) *nSplits = 0;
+		if (!fn_) return err_;
+		const int N = fn_->getNParams();
+		if (!grid_) {
+			std::vector<double> ranges;
+			parametricShape_->getRanges(&ranges);
+			std::unique_ptr<loco_grid::Grid> g(new loco_grid::Grid());
+			loco_grid::Status st = loco_grid::Grid::bootstrap(N, (int)basisType_, params_->bootstrapGridSize_, valueDim_, evalCorners_, ranges.data(),
+			                                                  &LCAdaptiveGrid::trampoline, this, g.get());
+			if (!st.ok) return LCError(st.msg);
+			if (!err_.isOK()) return err_;
+			LCErrorReturn(fn_->updateFromGraph(g->graph()));
+			grid_ = std::move(g);
+		}
+		for (int pass = 0; pass < maxPasses; pass++) {
+			std::vector<uint8_t> split;
+			std::vector<double> errMax;
+			LCErrorReturn(errorCheckBatch(&split, &errMax));
+			std::vector<SplitRequest> req;
+			LCErrorReturn(selectFromFlags(fn_.get(), split, params_->maxTreeDepth_, &req));
+			if (nPasses) *nPasses = pass + 1;
+			if (req.empty()) return LCError();
+			std::vector<int32_t> leaf, dir;
+			for (const SplitRequest &r : req) {
+				int d = r.direction;
+				if (params_->splitPolicy_ == LCAdaptiveSamplingParams::ERROR_BASED) {
+					loco_grid::Status st = grid_->optimalSplitDirection(r.leaf, &d);
+					if (!st.ok) return LCError(st.msg);
+				}
+				leaf.push_back(r.leaf);
+				dir.push_back(d);
+			}
+			loco_grid::Status st = grid_->refineLeaves(leaf.data(), dir.data(), (int64_t)leaf.size());
+			if (!st.ok) return LCError(st.msg);
+			if (!err_.isOK()) return err_;  // the function failed inside the surgery
+			if (nSplits) *nSplits += (int64_t)leaf.size();
+			LCErrorReturn(fn_->updateFromGraph(grid_->graph()));
+		}
+		return LCError("adaptiveSample: pass limit reached");
+	}
+	// the host grid behind adaptiveSample (nullptr before the first call)
+	loco_grid::Grid *getHostGrid() { return grid_.get(); }
 
 private:
 	static void trampoline(const double *p, double *out, void *user)
@@ -520,9 +596,11 @@ private:
 	LCAdaptiveSamplingParams *params_;
 	LCFunction *parametricShape_;
 	LCBasisFunction::LCBasisFunctionType basisType_;
+	bool evalCorners_ = false;
 	int valueDim_ = 1;
 	LCError err_;
 	std::unique_ptr<LCSampledFunction> fn_;
+	std::unique_ptr<loco_grid::Grid> grid_;
 };
 
 #ifdef LOCO_LC_NAMESPACE

@@ -6,6 +6,8 @@
 //   testFunctionLinearApproximation  TestExamples.cpp:185-211   sine-sum f, grid params (3,0.1,2,0) / (3,0.5,1,0), 21x21 sweep
 //   decideSplit                      LCAdaptiveGrid.cpp:578-626 CENTER_BASED and RANDOM_SAMPLES, batched over all leaves
 //   LCError behaviour                LCAdaptiveGridCell.cpp:438-454
+//   adaptiveSample                   LCAdaptiveGrid.cpp:481-545 the refinement loop, level-synchronous: error check on the GPU,
+//                                    refineCell (:629-914) by the host grid of include/loco_grid.hpp, incremental re-flatten
 //
 // usage:  test_facade <golden .pb> <dump file> [--host-only]
 // Unlike the reference's mains (which print and always exit 0) every check counts: exit status = failed checks.
@@ -357,13 +359,82 @@ static void updateFromGraphTest(bool hostOnly)
 	CHECK(worst <= 1e-12, "values equal the piecewise-linear interpolant of the refined state within 1e-12");
 }
 
+// LCAdaptiveGrid::adaptiveSample: the loop the reference's constructor runs (LCAdaptiveGrid.cpp:34, :481-545), here in
+// level-synchronous passes.  Host-only: the host grid is created and handed to the model, then the error check refuses
+// (no CPU path).  On the device: the loop terminates with no leaf flagged below the level limit, every split is accounted
+// for, and the interpolant of the refined grid is closer to the function than the bootstrap grid's.
+static void adaptiveSampleTest(bool hostOnly, LCBasisFunction::LCBasisFunctionType basis, LCAdaptiveSamplingParams::LCSplitPolicy policy,
+                               LCAdaptiveSamplingParams::LCErrorMetric metric)
+{
+	std::printf("adaptiveSample %s, %s split direction, %s error metric\n", basis == LCBasisFunction::CUBIC_BSPLINE ? "cubic" : "linear",
+	            policy == LCAdaptiveSamplingParams::ERROR_BASED ? "ERROR_BASED" : "CYCLIC", metric == LCAdaptiveSamplingParams::CENTER_BASED ? "CENTER_BASED" : "RANDOM_SAMPLES");
+	SineTestFunction f(2);
+	const double thr = 0.02;
+	const int maxDepth = 9, boot = 2;
+	LCAdaptiveSamplingParams params(maxDepth, thr, boot, 4, policy, metric);
+	LCAdaptiveGrid grid(&f, basis, &params, true, hostOnly ? LOCO_HOST_ONLY : 0);
+	CHECK(grid.status().isOK(), "grid construction");
+	if (!grid.status().isOK()) return;
+	LCSampledFunction *fn = grid.getSampledFunction();
+	const int64_t leaves0 = fn->getNLeaves(), samples0 = fn->getNSamples();
+	int passes = 0;
+	int64_t splits = 0;
+	if (hostOnly) {
+		LCError e = grid.adaptiveSample(&passes, &splits);
+		CHECK(!e.isOK() && e.internalDescription().find("no CPU path") != std::string::npos, "without a device the loop stops at its error check (no CPU path)");
+		CHECK(grid.getHostGrid() && grid.getHostGrid()->nLeaves() == leaves0 && grid.getHostGrid()->nSamples() == samples0 &&
+		      fn->getNLeaves() == leaves0 && fn->getNSamples() == samples0, "the host grid repeats the bootstrap phase and the model accepted its state");
+		// the surgery itself needs no device: split leaf 5 along dimension 1 and hand the new state to the model
+		loco_grid::Status st = grid.getHostGrid()->refineLeaf(5, 1);
+		CHECK(st.ok && fn->updateFromGraph(grid.getHostGrid()->graph()).isOK() && fn->getNLeaves() == leaves0 + 1 && fn->getNSamples() > samples0,
+		      "refineCell on the host grid + updateFromGraph: one more leaf, new mid samples");
+		return;
+	}
+	std::vector<double> exact, before, after;
+	CHECK(sweep2d(&f, 41, &exact).isOK() && sweep2d(fn, 41, &before).isOK(), "41x41 sweeps of the function and of the bootstrap interpolant");
+	srand(11);
+	LCError e = grid.adaptiveSample(&passes, &splits);
+	CHECK(e.isOK(), "adaptiveSample");
+	if (!e.isOK()) { std::printf("    %s\n", e.internalDescription().c_str()); return; }
+	std::printf("    %d passes, %lld splits: %lld -> %lld leaves, %lld -> %lld samples, %lld true-function evaluations by the host grid\n", passes, (long long)splits,
+	            (long long)leaves0, (long long)fn->getNLeaves(), (long long)samples0, (long long)fn->getNSamples(), (long long)grid.getHostGrid()->nFunctionEvaluations());
+	CHECK(passes > 2 && splits > 0 && fn->getNLeaves() == leaves0 + splits && grid.getHostGrid()->nLeaves() == fn->getNLeaves() &&
+	      grid.getHostGrid()->nSamples() == fn->getNSamples(), "every split adds one leaf; model and host grid agree on leaves and samples");
+	if (metric == LCAdaptiveSamplingParams::CENTER_BASED) {
+		std::vector<LCAdaptiveGrid::SplitRequest> req;
+		std::vector<double> err;
+		CHECK(LCAdaptiveGrid::selectSplits(fn, thr, maxDepth, &req, &err).isOK() && req.empty(), "after the loop no leaf below the level limit is flagged");
+		// leaves that are still above the threshold sit at the level limit
+		bool limit = true;
+		std::vector<double> box(4);
+		for (size_t l = 0; l < err.size(); l++)
+			if (!((err[l] - thr) <= 0)) {
+				loco_leaf_box(fn->handle(), (int32_t)l, box.data());
+				const long level = std::lround(std::log2(2.0 / (box[1] - box[0])) + std::log2(2.0 / (box[3] - box[2])));
+				limit = limit && level >= maxDepth;
+			}
+		CHECK(limit, "leaves whose centre error exceeds the threshold are at maxTreeDepth");
+	}
+	CHECK(sweep2d(fn, 41, &after).isOK(), "41x41 sweep of the refined interpolant");
+	double w0 = 0, w1 = 0, m0 = 0, m1 = 0;
+	for (size_t i = 0; i < exact.size() && i < after.size(); i++) {
+		w0 = std::max(w0, std::fabs(exact[i] - before[i])); w1 = std::max(w1, std::fabs(exact[i] - after[i]));
+		m0 += std::fabs(exact[i] - before[i]) / exact.size(); m1 += std::fabs(exact[i] - after[i]) / exact.size();
+	}
+	std::printf("    |approx - exact| over the sweep: bootstrap grid max %.4f mean %.4f, refined grid max %.4f mean %.4f\n", w0, m0, w1, m1);
+	CHECK(after.size() == exact.size() && m1 < 0.5 * m0, "the refined interpolant is on average at least twice as close to the function as the bootstrap grid's");
+}
+
 int main(int argc, char **argv)
 {
 	if (argc < 3) { std::printf("usage: %s <golden .pb> <dump file> [--host-only]\n", argv[0]); return 2; }
 	const bool hostOnly = argc > 3 && !std::strcmp(argv[3], "--host-only");
 	protoTest(argv[1], argv[2], hostOnly);
 	updateFromGraphTest(hostOnly);
+	adaptiveSampleTest(hostOnly, LCBasisFunction::CUBIC_BSPLINE, LCAdaptiveSamplingParams::ERROR_BASED, LCAdaptiveSamplingParams::CENTER_BASED);
 	if (!hostOnly) {
+		adaptiveSampleTest(false, LCBasisFunction::LINEAR_BSPLINE, LCAdaptiveSamplingParams::CYCLIC, LCAdaptiveSamplingParams::CENTER_BASED);
+		adaptiveSampleTest(false, LCBasisFunction::LINEAR_BSPLINE, LCAdaptiveSamplingParams::ERROR_BASED, LCAdaptiveSamplingParams::RANDOM_SAMPLES);
 		linearPrecisionTest(1, LCBasisFunction::CUBIC_BSPLINE, 2);
 		linearPrecisionTest(3, LCBasisFunction::CUBIC_BSPLINE, 1);
 		linearPrecisionTest(2, LCBasisFunction::LINEAR_BSPLINE, 2);

@@ -9,7 +9,8 @@ LIBDIR = os.path.join(ROOT, "locointerpolate_b200")
 
 
 def build(force: bool = False) -> str:
-    deps = [SRC, os.path.join(ROOT, "include", "loco_lc.hpp"), os.path.join(ROOT, "include", "loco_b200.h")]
+    deps = [SRC, os.path.join(ROOT, "include", "loco_lc.hpp"), os.path.join(ROOT, "include", "loco_grid.hpp"),
+            os.path.join(ROOT, "include", "loco_b200.h")]
     if not force and os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
         return EXE
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), SRC, "-o", EXE,

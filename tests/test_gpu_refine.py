@@ -83,3 +83,32 @@ def test_refinement_loop_on_one_handle_updated_incrementally():
         a, la, sa = m.eval(q)
         b, lb, sb = fresh.eval(q)
         assert np.array_equal(la, lb) and np.array_equal(sa, sb) and np.array_equal(a, b, equal_nan=True), path
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref (the compiled reference) is not built")
+@pytest.mark.parametrize("basis,max_level,threshold", [(capi.LINEAR, 8, 0.05), (capi.CUBIC, 7, 0.1)])
+def test_refinement_loop_with_native_surgery(basis, max_level, threshold):
+    """The loop without the reference library in it: error check on the device, surgery by the native host grid
+    (include/loco_grid.hpp, through tests/nativegrid.py), one handle updated incrementally.  The same loop with the
+    reference's refineCell as the host makes the same decisions and ends in the same grid."""
+    import nativegrid
+    from test_native_refine import assert_same_grid
+    ref = refapi.RefGrid(2, basis, False, 0, threshold, 2)
+    g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
+    nat = nativegrid.NativeGrid.bootstrap(2, basis, 2, g0.domain, ref.true_values)
+    log_nat = refine.adaptive_sample_passes(None, nat.refine, threshold, max_level, get_graph=nat.graph, device=0)
+    log_ref = refine.adaptive_sample_passes(None, ref.refine, threshold, max_level, device=0,
+                                            get_graph=lambda: oracleapi.graph_from_ref(ref.sampled_function().graph()))
+    assert [(p["leaves"], p["flagged"]) for p in log_nat] == [(p["leaves"], p["flagged"]) for p in log_ref]
+    assert np.allclose([p["max_center_error"] for p in log_nat], [p["max_center_error"] for p in log_ref], rtol=0, atol=1e-13)
+    assert log_nat[-1]["flagged"] == 0 and log_nat[-1]["leaves"] > 16 and max(p["reused_leaves"] for p in log_nat) > 0
+    assert_same_grid(oracleapi.graph_from_ref(ref.sampled_function().graph()), nat.graph(), "after the loop")
+    # the native grid's model evaluates like the reference's LCSampledFunction over the reference-refined grid
+    m = capi.Model.from_graph(nat.graph(), device=0)
+    fn = ref.sampled_function()
+    q = np.random.default_rng(3).random((4000, 2))
+    out, leaf, status = m.eval(q)
+    r_out, r_leaf, r_status = fn.eval(q)
+    assert np.array_equal(leaf, r_leaf) and np.array_equal(status, r_status)
+    ok = status == 0
+    assert np.abs(out[ok] - r_out[ok]).max() <= 1e-12 * max(1.0, np.abs(r_out[ok]).max())
