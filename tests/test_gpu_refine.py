@@ -101,7 +101,9 @@ def test_refinement_loop_with_native_surgery(basis, max_level, threshold):
                                             get_graph=lambda: oracleapi.graph_from_ref(ref.sampled_function().graph()))
     assert [(p["leaves"], p["flagged"]) for p in log_nat] == [(p["leaves"], p["flagged"]) for p in log_ref]
     assert np.allclose([p["max_center_error"] for p in log_nat], [p["max_center_error"] for p in log_ref], rtol=0, atol=1e-13)
-    assert log_nat[-1]["flagged"] == 0 and log_nat[-1]["leaves"] > 16 and max(p["reused_leaves"] for p in log_nat) > 0
+    assert log_nat[-1]["flagged"] == 0 and log_nat[-1]["leaves"] > 16
+    if basis == capi.CUBIC:   # evaluation cells (the derived data the incremental update carries over) exist on cubic scalar trees
+        assert max(p["reused_leaves"] for p in log_nat) > 0
     assert_same_grid(oracleapi.graph_from_ref(ref.sampled_function().graph()), nat.graph(), "after the loop")
     # the native grid's model evaluates like the reference's LCSampledFunction over the reference-refined grid
     m = capi.Model.from_graph(nat.graph(), device=0)
