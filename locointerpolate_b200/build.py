@@ -18,6 +18,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libloco_b200.so")
+# the host-only companion library (C ABI include/loco_grid.h over include/loco_grid.hpp: the builder's grid state and
+# refineCell's topology surgery).  No CUDA in it: g++ alone, kept apart from the kernels' library.
+GRID_LIB = os.path.join(HERE, "libloco_grid.so")
+GRID_SOURCES = [os.path.join(HERE, "hostsrc", "loco_grid_capi.cpp")]
+GRID_DEPS = GRID_SOURCES + [os.path.join(HERE, "..", "include", h) for h in ("loco_grid.h", "loco_grid.hpp", "loco_b200.h")]
 
 SOURCES = ["loco_capi.cu", "loco_kernels.cu", "loco_tiles.cu", "loco_sorted.cu", "loco_bucket.cu", "loco_tensor.cu", "loco_errgen.cu", "loco_mesh.cu", "loco_mesh_mma.cu", "loco_mesh_gen.cu", "loco_proto.cpp", "loco_flatten.cpp", "loco_bootstrap.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -83,5 +88,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_grid(force: bool = False) -> str:
+    """libloco_grid.so: g++ -shared of hostsrc/loco_grid_capi.cpp (host-only, no nvcc)"""
+    stamp = os.path.join(OBJ, "grid_stamp")
+    dig = _digest(GRID_DEPS)
+    if not force and os.path.exists(GRID_LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return GRID_LIB
+    os.makedirs(OBJ, exist_ok=True)
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Werror", "-fPIC", "-shared", "-I" + os.path.join(HERE, "..", "include"), *GRID_SOURCES, "-o", GRID_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for libloco_grid.so:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return GRID_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_grid(force="--force" in sys.argv))

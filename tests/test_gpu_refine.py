@@ -89,14 +89,14 @@ def test_refinement_loop_on_one_handle_updated_incrementally():
 @pytest.mark.parametrize("basis,max_level,threshold", [(capi.LINEAR, 8, 0.05), (capi.CUBIC, 7, 0.1)])
 def test_refinement_loop_with_native_surgery(basis, max_level, threshold):
     """The loop without the reference library in it: error check on the device, surgery by the native host grid
-    (include/loco_grid.hpp, through tests/nativegrid.py), one handle updated incrementally.  The same loop with the
+    (include/loco_grid.hpp, through locointerpolate_b200/grid.py), one handle updated incrementally.  The same loop with the
     reference's refineCell as the host makes the same decisions and ends in the same grid."""
-    import nativegrid
+    from locointerpolate_b200.grid import HostGrid, adaptive_sample
     from test_native_refine import assert_same_grid
     ref = refapi.RefGrid(2, basis, False, 0, threshold, 2)
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid.bootstrap(2, basis, 2, g0.domain, ref.true_values)
-    log_nat = refine.adaptive_sample_passes(None, nat.refine, threshold, max_level, get_graph=nat.graph, device=0)
+    nat = HostGrid.bootstrap(2, basis, 2, g0.domain, ref.true_values)
+    log_nat = adaptive_sample(nat, threshold, max_level, device=0)
     log_ref = refine.adaptive_sample_passes(None, ref.refine, threshold, max_level, device=0,
                                             get_graph=lambda: oracleapi.graph_from_ref(ref.sampled_function().graph()))
     assert [(p["leaves"], p["flagged"]) for p in log_nat] == [(p["leaves"], p["flagged"]) for p in log_ref]

@@ -25,6 +25,29 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(L, name), name
 
 
+def test_grid_abi_exports_every_declared_symbol():
+    """the host-only companion library (include/loco_grid.h: the builder's grid state and refineCell) likewise"""
+    from locointerpolate_b200 import build as product_build, grid
+    header = open(os.path.join(ROOT, "include", "loco_grid.h")).read()
+    declared = set(re.findall(r"\b(loco_grid_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(grid.SYMBOLS), (declared ^ set(grid.SYMBOLS))
+    L = ctypes.CDLL(product_build.build_grid())
+    for name in declared:
+        assert hasattr(L, name), name
+    # constructor errors come back through loco_grid_last_error(NULL)
+    with pytest.raises(capi.LocoError, match="number of levels must be positive"):
+        grid.HostGrid.bootstrap(2, capi.LINEAR, -1, [0, 1, 0, 1], lambda p: p[:, 0])
+    g = grid.HostGrid.bootstrap(2, capi.CUBIC, 1, [0, 1, 0, 1], lambda p: p[:, 0])
+    with pytest.raises(capi.LocoError, match="split direction out of range"):
+        g.refine(0, 2)
+    with pytest.raises(capi.LocoError, match="leaf index out of range"):
+        g.refine(4, 0)
+    with pytest.raises(capi.LocoError, match="descending"):
+        g.refine_pass([0, 1], [0, 0])
+    g.refine_pass([3, 1], [0, 1])
+    assert g.num_leaves() == 6
+
+
 def test_no_cpu_path():
     """Without a usable device, construction fails; a host-only handle refuses to evaluate."""
     pb = os.path.join(ROOT, "tests", "golden", "c1_lin2d_boot2.pb")

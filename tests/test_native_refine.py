@@ -1,4 +1,5 @@
-"""The native builder state and refineCell (include/loco_grid.hpp) against the compiled reference
+"""The native builder state and refineCell (include/loco_grid.hpp through its C ABI include/loco_grid.h and
+locointerpolate_b200/grid.py) against the compiled reference
 (oracle/_ref: LCAdaptiveGrid::bootstrapSample / refineCell, LCAdaptiveGrid.cpp:256-456, 629-914) on the CPU.
 
 Grids are compared as SETS -- samples by centre, basis functions by (centre, support) key, per-cell sample sets, boxes, centre
@@ -7,8 +8,8 @@ order are not defined by it (the weights are sums of dyadic fractions and come o
 import numpy as np
 import pytest
 
-import nativegrid
 from locointerpolate_b200 import capi, refine
+from locointerpolate_b200.grid import HostGrid
 from oracle import oracleapi, refapi
 
 pytestmark = pytest.mark.skipif(not refapi.available(), reason="oracle/_ref (the compiled reference) is not built")
@@ -64,7 +65,7 @@ def assert_same_grid(ga, gb, tag=""):
 def test_native_bootstrap_equals_the_reference_builder(N, basis, boot, eval_corners):
     ref = refapi.RefGrid(N, basis, False, 0, 0.5, boot, eval_corners=eval_corners)
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values, eval_corners=eval_corners)
+    nat = HostGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values, eval_corners=eval_corners)
     g1 = nat.graph()
     assert_same_grid(g0, g1)
     # beyond the set comparison: the same sample ORDER (samples_ order = proto ids), border-cell order and value sharing
@@ -84,7 +85,7 @@ def test_native_refine_cell_equals_the_reference(N, basis, boot, steps, seed, st
     """the same random refineCell sequence (TestExamples.cpp:225-240 style) on the reference's grid and on the native one"""
     ref = refapi.RefGrid(N, basis, False, 0, 0.5, boot)
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid(g0, ref.true_values) if start == "graph" else nativegrid.NativeGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values)
+    nat = HostGrid.from_graph(g0, ref.true_values) if start == "graph" else HostGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values)
     rng = np.random.default_rng(seed)
     for step in range(steps):
         L = ref.num_leaves()
@@ -106,7 +107,7 @@ def test_native_refine_cell_equals_the_reference_3d(basis, sequence):
     sequences are checked through linear precision below)"""
     ref = refapi.RefGrid(3, basis, False, 0, 0.5, 1)
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid(g0, ref.true_values)
+    nat = HostGrid.from_graph(g0, ref.true_values)
     for leaf, direction in sequence:
         ref.refine(leaf, direction)
         nat.refine(leaf, direction)
@@ -119,7 +120,7 @@ def test_native_refinement_keeps_linear_precision(N, basis, boot, steps):
     interpolant of a LINEAR function is that function; evaluated with the CPU restatement on the native grid's graph"""
     ref = refapi.RefGrid(N, basis, True, 0, 0.5, boot)   # linear_fn=True: the function being sampled is linear
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values)
+    nat = HostGrid.bootstrap(N, basis, boot, g0.domain, ref.true_values)
     rng = np.random.default_rng(11)
     dom = g0.domain.reshape(N, 2)
     for step in range(steps):
@@ -143,7 +144,7 @@ def test_level_synchronous_loop_with_native_surgery(basis, max_level, threshold)
     The same passes driven with the REFERENCE's refineCell give the same grid."""
     ref = refapi.RefGrid(2, basis, False, 0, threshold, 2)
     g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
-    nat = nativegrid.NativeGrid.bootstrap(2, basis, 2, g0.domain, ref.true_values)
+    nat = HostGrid.bootstrap(2, basis, 2, g0.domain, ref.true_values)
 
     def model_of(graph_fn):
         def get_model():
@@ -165,5 +166,5 @@ def test_optimal_split_direction():
     """ERROR_BASED split policy (getOptimalSplitDirection, LCAdaptiveGridCell.cpp:977-1041) on a function that varies in one
     direction only: the direction of the variation is chosen in every leaf"""
     for vary in (0, 1, 2):
-        nat = nativegrid.NativeGrid.bootstrap(3, capi.LINEAR, 1, [0, 1, 0, 2, -1, 1], lambda p, v=vary: np.sin(3 * p[:, v]))
+        nat = HostGrid.bootstrap(3, capi.LINEAR, 1, [0, 1, 0, 2, -1, 1], lambda p, v=vary: np.sin(3 * p[:, v]))
         assert [nat.optimal_direction(l) for l in range(nat.num_leaves())] == [vary] * 8
