@@ -34,6 +34,7 @@
 #include <cmath>
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -453,15 +454,44 @@ public:
 			bf.swap(kept);
 		}
 		// every sample of the grid hands its function of a grouped key over to the group (:853-863, extractGroupBasisFunctions)
-		if (!groups.empty())
-			for (Sample &smp : samples_)
-				for (Group &gr : groups)
-					for (size_t b = 0; b < smp.bf.size(); b++)
-						if (sameKey(gr.c, gr.s, smp.bf[b].c, smp.bf[b].s)) {
-							group_add(gr, smp, smp.bf[b].w);
-							smp.bf.erase(smp.bf.begin() + (long)b);
-							break;
-						}
+		// (the reference looks every group up in every sample's map; here the groups are indexed by the bucket of their first
+		// centre coordinate, buckets twice EPSILON wide, so the keys that can be equal to a function are in three buckets)
+		if (!groups.empty()) {
+			const double bucket_width = 2 * kEpsilon;
+			std::unordered_map<int64_t, std::vector<int32_t>> by_bucket;
+			for (size_t k = 0; k < groups.size(); k++) by_bucket[(int64_t)std::floor(groups[k].c[0] / bucket_width)].push_back((int32_t)k);
+			std::vector<uint8_t> taken(groups.size());
+			std::vector<double> lo((size_t)N, 1e300), hi((size_t)N, -1e300);  // box of the grouped centres: most functions of the grid are outside
+			for (const Group &gr : groups)
+				for (int d = 0; d < N; d++) {
+					lo[(size_t)d] = std::min(lo[(size_t)d], gr.c[(size_t)d] - kEpsilon);
+					hi[(size_t)d] = std::max(hi[(size_t)d], gr.c[(size_t)d] + kEpsilon);
+				}
+			for (Sample &smp : samples_) {
+				std::fill(taken.begin(), taken.end(), 0);
+				size_t kept = 0;
+				for (size_t b = 0; b < smp.bf.size(); b++) {
+					bool inside = true;
+					for (int d = 0; d < N && inside; d++) inside = smp.bf[b].c[(size_t)d] > lo[(size_t)d] && smp.bf[b].c[(size_t)d] < hi[(size_t)d];
+					int32_t hit = -1;
+					const int64_t bucket = inside ? (int64_t)std::floor(smp.bf[b].c[0] / bucket_width) : 0;
+					for (int64_t probe = bucket - 1; inside && probe <= bucket + 1 && hit < 0; probe++) {
+						auto it = by_bucket.find(probe);
+						if (it == by_bucket.end()) continue;
+						for (int32_t k : it->second)
+							if (!taken[(size_t)k] && sameKey(groups[(size_t)k].c, groups[(size_t)k].s, smp.bf[b].c, smp.bf[b].s)) { hit = k; break; }
+					}
+					if (hit >= 0) {  // one function per sample and group, as a lookup in the sample's map gives
+						taken[(size_t)hit] = 1;
+						group_add(groups[(size_t)hit], smp, smp.bf[b].w);
+						continue;
+					}
+					if (kept != b) smp.bf[kept] = std::move(smp.bf[b]);
+					kept++;
+				}
+				smp.bf.resize(kept);
+			}
+		}
 		// each group is re-attached, multilinearly weighted, to the corner samples of the intersection of the cells adjacent to
 		// the group's weighted sample centre (:865-893)
 		for (const Group &gr : groups) {
@@ -777,7 +807,10 @@ private:
 	}
 	static bool sameKey(const std::vector<double> &c1, const std::vector<double> &s1, const std::vector<double> &c2, const std::vector<double> &s2)
 	{
-		return distance(c1, c2) < kEpsilon && distance(s1, s2) < kEpsilon;  // LCBasisFunctionKey::operator== (LCBasisFunction.h:88-92)
+		// LCBasisFunctionKey::operator== (LCBasisFunction.h:88-92): both Euclidean distances below EPSILON.  A coordinate that
+		// differs by EPSILON or more already decides it (the distance is at least any coordinate difference).
+		if (!(std::abs(c1[0] - c2[0]) < kEpsilon) || !(std::abs(s1[0] - s2[0]) < kEpsilon)) return false;
+		return distance(c1, c2) < kEpsilon && distance(s1, s2) < kEpsilon;
 	}
 	void addBasisFunction(int32_t s, Basis f)  // LCSample::addBasisFunction (LCSample.cpp:89-103)
 	{
