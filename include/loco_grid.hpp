@@ -574,6 +574,11 @@ public:
 			x.cell_child2.push_back(c.leaf ? -1 : pos[(size_t)c.child2]);
 		}
 		for (int32_t ci : border_) put_cell(cells_[(size_t)ci], x.border_ranges, x.border_center, x.border_off, x.border_sample, x.border_copies);
+		auto have_centers = [&](const std::vector<int32_t> &ids) {
+			for (int32_t ci : ids)
+				if (cells_[(size_t)ci].leaf && cells_[(size_t)ci].center_row < 0) return false;
+			return true;
+		};
 		loco_graph_t &g = x.g;
 		g = loco_graph_t();
 		g.n_params = N;
@@ -593,13 +598,13 @@ public:
 		g.cell_split_dir = x.cell_split_dir.data();
 		g.cell_split_val = x.cell_split_val.data();
 		g.cell_child2 = x.cell_child2.data();
-		g.cell_center_value = x.cell_center.data();
+		g.cell_center_value = have_centers(order) ? x.cell_center.data() : nullptr;  // a grid taken over without centre values has none to give
 		g.cell_sample_offset = x.cell_off.data();
 		g.cell_sample = x.cell_sample.data();
 		g.cell_sample_value = x.cell_copies.data();
 		g.n_border_cells = (int64_t)border_.size();
 		g.border_ranges = x.border_ranges.data();
-		g.border_center_value = x.border_center.data();
+		g.border_center_value = have_centers(border_) ? x.border_center.data() : nullptr;
 		g.border_sample_offset = x.border_off.data();
 		g.border_sample = x.border_sample.data();
 		g.border_sample_value = x.border_copies.data();
