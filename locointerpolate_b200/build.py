@@ -95,7 +95,9 @@ def build_grid(force: bool = False) -> str:
     if not force and os.path.exists(GRID_LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return GRID_LIB
     os.makedirs(OBJ, exist_ok=True)
-    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    # g++ from PATH, not $CXX: this image's CXX wrapper links libstdc++ statically (see oracle/Makefile), and a shared object
+    # with a private libstdc++ must not meet the process's own copy
+    cxx = os.environ.get("LOCO_CXX") or shutil.which("g++") or "g++"
     cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Werror", "-fPIC", "-shared", "-I" + os.path.join(HERE, "..", "include"), *GRID_SOURCES, "-o", GRID_LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
