@@ -541,6 +541,11 @@ public:
 			}
 			x.bf_off.push_back((int64_t)x.bf_weight.size());
 		}
+		// per-cell value copies are exported only if some cell holds a copy that is not its sample's own value object (grids
+		// taken over from arrays with such copies): a natively built grid hands over none (E x D doubles saved)
+		bool with_copies = false;
+		for (const Cell &c : cells_)
+			for (const auto &e : c.samples) with_copies = with_copies || e.second != samples_[(size_t)e.first].row;
 		auto put_cell = [&](const Cell &c, std::vector<double> &ranges, std::vector<double> &center, std::vector<int64_t> &off, std::vector<int32_t> &smp,
 		                    std::vector<double> &copies) {
 			ranges.insert(ranges.end(), c.box.begin(), c.box.end());
@@ -550,7 +555,7 @@ public:
 			std::sort(sorted.begin(), sorted.end());
 			for (const auto &e : sorted) {
 				smp.push_back(e.first);
-				copies.insert(copies.end(), values_.begin() + (size_t)e.second * D, values_.begin() + ((size_t)e.second + 1) * D);
+				if (with_copies) copies.insert(copies.end(), values_.begin() + (size_t)e.second * D, values_.begin() + ((size_t)e.second + 1) * D);
 			}
 			off.push_back((int64_t)smp.size());
 		};
@@ -601,13 +606,13 @@ public:
 		g.cell_center_value = have_centers(order) ? x.cell_center.data() : nullptr;  // a grid taken over without centre values has none to give
 		g.cell_sample_offset = x.cell_off.data();
 		g.cell_sample = x.cell_sample.data();
-		g.cell_sample_value = x.cell_copies.data();
+		g.cell_sample_value = with_copies ? x.cell_copies.data() : nullptr;
 		g.n_border_cells = (int64_t)border_.size();
 		g.border_ranges = x.border_ranges.data();
 		g.border_center_value = have_centers(border_) ? x.border_center.data() : nullptr;
 		g.border_sample_offset = x.border_off.data();
 		g.border_sample = x.border_sample.data();
-		g.border_sample_value = x.border_copies.data();
+		g.border_sample_value = with_copies ? x.border_copies.data() : nullptr;
 		return g;
 	}
 

@@ -149,11 +149,12 @@ class HostGrid:
             sample_value=_arr(s.sample_value, S * D, f), sample_value_group=_arr(s.sample_value_group, S, i32), bf_offset=bf_off,
             bf_center=_arr(s.bf_center, B * N, f), bf_support=_arr(s.bf_support, B * N, f), bf_weight=_arr(s.bf_weight, B, f),
             cell_ranges=_arr(s.cell_ranges, Cn * 2 * N, f), cell_split_dir=_arr(s.cell_split_dir, Cn, i32), cell_split_val=_arr(s.cell_split_val, Cn, f),
-            cell_child2=_arr(s.cell_child2, Cn, i32), cell_center_value=_arr(s.cell_center_value, Cn * D, f), cell_sample_offset=c_off,
-            cell_sample=_arr(s.cell_sample, E, i32), cell_sample_value=_arr(s.cell_sample_value, E * D, f),
-            border_ranges=_arr(s.border_ranges, Bc * 2 * N, f) if Bc else None, border_center_value=_arr(s.border_center_value, Bc * D, f) if Bc else None,
+            cell_child2=_arr(s.cell_child2, Cn, i32), cell_center_value=_arr(s.cell_center_value, Cn * D, f) if s.cell_center_value else None,
+            cell_sample_offset=c_off,
+            cell_sample=_arr(s.cell_sample, E, i32), cell_sample_value=_arr(s.cell_sample_value, E * D, f) if s.cell_sample_value else None,
+            border_ranges=_arr(s.border_ranges, Bc * 2 * N, f) if Bc else None, border_center_value=_arr(s.border_center_value, Bc * D, f) if Bc and s.border_center_value else None,
             border_sample_offset=b_off if Bc else None, border_sample=_arr(s.border_sample, Eb, i32) if Bc else None,
-            border_sample_value=_arr(s.border_sample_value, Eb * D, f) if Bc else None).normalise()
+            border_sample_value=_arr(s.border_sample_value, Eb * D, f) if Bc and s.border_sample_value else None).normalise()
 
 
 def adaptive_sample(grid: HostGrid, threshold: float, max_level: int, device: int = 0, error_based_direction: bool = False,
