@@ -171,6 +171,19 @@ int ref_grid_refine(void *gp, int leaf, int dir)
 	return g->grid->refineCell(leafs[leaf], dir, &affected).isOK() ? 0 : -2;
 }
 
+// LCAdaptiveGridCell::getOptimalSplitDirection (LCAdaptiveGridCell.cpp:977-1041; the ERROR_BASED split policy,
+// LCAdaptiveGrid::decideSplitDirection :556-557) for the leaf-th leaf; -1 if the reference reports an error.
+int ref_grid_optimal_direction(void *gp, int leaf)
+{
+	CoutMute mute;
+	RefGrid *g = (RefGrid *)gp;
+	std::vector<LCAdaptiveGridCell *> leafs;
+	g->grid->getRoot()->getAllLeafCells(&leafs);
+	if (leaf < 0 || leaf >= (int)leafs.size()) return -1;
+	int dir = -1;
+	return leafs[leaf]->getOptimalSplitDirection(&dir).isOK() ? dir : -1;
+}
+
 // True function the grid samples, in ORIGINAL parameter space (LCRealFunction.cpp:50-77).
 void ref_grid_true_values(void *gp, const double *q, long Q, double *out)
 {

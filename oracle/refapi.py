@@ -36,6 +36,7 @@ def lib():
         L.ref_grid_num_leaves.argtypes = [vp]
         L.ref_grid_refine_random.argtypes = [vp, C.c_uint, i, i]
         L.ref_grid_refine.argtypes = [vp, i, i]
+        L.ref_grid_optimal_direction.argtypes = [vp, i]
         L.ref_grid_true_values.argtypes = [vp, vp, l, vp]
         L.ref_fn_from_grid.restype = vp
         L.ref_fn_from_grid.argtypes = [vp]
@@ -120,6 +121,10 @@ class RefGrid:
         r = lib().ref_grid_refine(self.h, leaf, direction)
         if r != 0:
             raise RuntimeError(f"reference refineCell failed ({r})")
+
+    def optimal_direction(self, leaf):
+        """LCAdaptiveGridCell::getOptimalSplitDirection of the leaf-th leaf (-1: the reference reports an error)"""
+        return lib().ref_grid_optimal_direction(self.h, int(leaf))
 
     def true_values(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.N)

@@ -149,6 +149,24 @@ def test_level_synchronous_loop_with_native_surgery(basis, max_level, threshold)
     assert_same_grid(oracleapi.graph_from_ref(ref.sampled_function().graph()), nat.graph(), "after the loop")
 
 
+@pytest.mark.parametrize("N,basis,boot,steps", [(2, capi.CUBIC, 2, 25), (2, capi.LINEAR, 2, 25), (3, capi.LINEAR, 1, 15)])
+def test_optimal_split_direction_equals_the_reference(N, basis, boot, steps):
+    """ERROR_BASED split policy on randomly refined grids: every leaf, against LCAdaptiveGridCell::getOptimalSplitDirection"""
+    ref = refapi.RefGrid(N, basis, False, 0, 0.5, boot)
+    g0 = oracleapi.graph_from_ref(ref.sampled_function().graph())
+    nat = HostGrid.from_graph(g0, ref.true_values)
+    rng = np.random.default_rng(21)
+    for step in range(steps):
+        L = ref.num_leaves()
+        want = [ref.optimal_direction(l) for l in range(L)]
+        assert min(want) >= 0
+        assert [nat.optimal_direction(l) for l in range(L)] == want, step
+        leaf = int(rng.integers(0, L))
+        ref.refine(leaf, want[leaf])
+        nat.refine(leaf, want[leaf])
+    assert_same_grid(oracleapi.graph_from_ref(ref.sampled_function().graph()), nat.graph())
+
+
 def test_optimal_split_direction():
     """ERROR_BASED split policy (getOptimalSplitDirection, LCAdaptiveGridCell.cpp:977-1041) on a function that varies in one
     direction only: the direction of the variation is chosen in every leaf"""
