@@ -25,6 +25,16 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(L, name), name
 
 
+def test_headers_compile_as_c(tmp_path):
+    """the boundary is a C ABI: both headers are valid C99 (plain pointers and sizes, no C++ in the signatures)"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "loco_b200.h"\n#include "loco_grid.h"\nint main(void) { loco_model_t *m = 0; loco_grid_t *g = 0; loco_graph_t gr; (void)m; (void)g; (void)gr; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "abi.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_grid_abi_exports_every_declared_symbol():
     """the host-only companion library (include/loco_grid.h: the builder's grid state and refineCell) likewise"""
     from locointerpolate_b200 import build as product_build, grid
